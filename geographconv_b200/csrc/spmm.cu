@@ -1,0 +1,522 @@
+// spmm.cu -- CSR x dense SpMM for sm_100a:  C = epilogue(A . B).
+//
+// Replaces theano.sparse.structured_dot (reference gcnmodel.py:39,130,153 and its gradient): the
+// hot loop of the GCN (A_hat.H), the first-layer projection (X.W0) and the transposed product
+// X^T.dz all run through the kernels in this file.
+//
+// Work decomposition: the host plan (gcnb_csr_plan) cuts every row into "items" of at most
+// `chunk` nonzeros.  One warp owns one item: lanes are spread across the feature columns
+// (float4 per lane, NCHUNK float4s per lane => up to 512 columns per pass), the warp walks the
+// item's nonzeros in CSR order and accumulates val * B[col, :] in registers -- a segmented,
+// order-preserving reduction over the nonzeros of the row.  Single-item rows run the fused
+// epilogue and store once; multi-item ("long") rows store per-item partial sums that
+// spmm_fixup_kernel adds in item order, so results do not depend on scheduling.
+//
+// Two gather engines, selected per context ("spmm_variant"):
+//   0  LDG.128 register gather: U nonzeros x NCHUNK 128-bit loads in flight per warp.
+//   1  bulk-copy (TMA engine, cp.async.bulk -> SASS UBLKCP) staged gather: each warp owns a ring
+//      of shared-memory row slots armed with mbarriers; one lane issues a 1-D bulk copy per
+//      gathered row, the warp consumes rows from shared memory with conflict-free LDS.128.
+//      Persistent CTAs (one per SM) pull items from an atomic counter.
+//
+// HBM model: per nonzero one K-wide fp32 row of B is read (K*4 B) plus 8 B of CSR;
+// per row K*4 B are written.
+#include "common.cuh"
+
+namespace {
+
+struct SpmmParams {
+  const int4* items;
+  int n_items;
+  const int* col;
+  const float* val;
+  const float* B;
+  int ldb;
+  float* C;
+  int ldc;
+  int K;
+  int col0;  // first column of this pass (multiple of 4)
+  int nf4;   // float4s per row in this pass
+  float* partial;
+  int ldp;  // floats per partial slot
+  const float* bias;
+  int act;
+  int softmax;
+  int accumulate;
+  uint32_t thresh;  // dropout keep threshold (0 => no dropout)
+  float scale;
+  uint64_t seed;
+  int64_t row0;
+  float* logits;
+  const int* long_rows;
+  int n_long;
+  int* counter;
+};
+
+constexpr int kWarpsPerCta = 8;
+
+// ---------------------------------------------------------------------------------------
+// fused epilogue: the warp holds one output row (acc[ch] = float4 number lane + 32*ch)
+// ---------------------------------------------------------------------------------------
+template <int NCHUNK>
+__device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, float4 (&acc)[NCHUNK], int lane) {
+  float v[NCHUNK][4];
+#pragma unroll
+  for (int ch = 0; ch < NCHUNK; ++ch) {
+    v[ch][0] = acc[ch].x; v[ch][1] = acc[ch].y; v[ch][2] = acc[ch].z; v[ch][3] = acc[ch].w;
+  }
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int ch = 0; ch < NCHUNK; ++ch) {
+      const int f4 = lane + 32 * ch;
+      if (f4 < p.nf4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + p.col0) + f4);
+        v[ch][0] += b.x; v[ch][1] += b.y; v[ch][2] += b.z; v[ch][3] += b.w;
+      }
+    }
+  }
+  if (p.softmax) {
+    if (p.logits != nullptr) {
+#pragma unroll
+      for (int ch = 0; ch < NCHUNK; ++ch) {
+        const int f4 = lane + 32 * ch;
+        if (f4 < p.nf4) {
+          float4 o;
+          const int c = p.col0 + 4 * f4;
+          o.x = c + 0 < p.K ? v[ch][0] : 0.f; o.y = c + 1 < p.K ? v[ch][1] : 0.f;
+          o.z = c + 2 < p.K ? v[ch][2] : 0.f; o.w = c + 3 < p.K ? v[ch][3] : 0.f;
+          reinterpret_cast<float4*>(p.logits + (size_t)row * p.ldc + p.col0)[f4] = o;
+        }
+      }
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int ch = 0; ch < NCHUNK; ++ch) {
+      const int c = p.col0 + 4 * (lane + 32 * ch);
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (lane + 32 * ch < p.nf4 && c + e < p.K) m = fmaxf(m, v[ch][e]);
+    }
+    m = warp_max(m);
+    float s = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < NCHUNK; ++ch) {
+      const int c = p.col0 + 4 * (lane + 32 * ch);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool ok = lane + 32 * ch < p.nf4 && c + e < p.K;
+        v[ch][e] = ok ? expf(v[ch][e] - m) : 0.f;
+        s += v[ch][e];
+      }
+    }
+    s = warp_sum(s);
+#pragma unroll
+    for (int ch = 0; ch < NCHUNK; ++ch)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[ch][e] = v[ch][e] / s;
+  } else {
+#pragma unroll
+    for (int ch = 0; ch < NCHUNK; ++ch) {
+      const int f4 = lane + 32 * ch;
+      const int c = p.col0 + 4 * f4;
+      if (f4 < p.nf4) {
+        if (p.act != GCNB_ACT_LINEAR) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[ch][e] = act_apply(p.act, v[ch][e]);
+        }
+        if (p.thresh != 0u) {
+          const uint4 r = dropout_draw(p.seed, p.row0 + row, (uint32_t)(c >> 2));
+          v[ch][0] = r.x < p.thresh ? v[ch][0] * p.scale : 0.f;
+          v[ch][1] = r.y < p.thresh ? v[ch][1] * p.scale : 0.f;
+          v[ch][2] = r.z < p.thresh ? v[ch][2] * p.scale : 0.f;
+          v[ch][3] = r.w < p.thresh ? v[ch][3] * p.scale : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (c + e >= p.K) v[ch][e] = 0.f;  // padding columns stay zero
+      }
+    }
+  }
+  float4* crow = reinterpret_cast<float4*>(p.C + (size_t)row * p.ldc + p.col0);
+#pragma unroll
+  for (int ch = 0; ch < NCHUNK; ++ch) {
+    const int f4 = lane + 32 * ch;
+    if (f4 < p.nf4) {
+      float4 o = make_float4(v[ch][0], v[ch][1], v[ch][2], v[ch][3]);
+      if (p.accumulate) {
+        const float4 old = crow[f4];
+        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+      }
+      st_stream_f4(crow + f4, o);
+    }
+  }
+}
+
+template <int NCHUNK>
+__device__ __forceinline__ void spmm_store_item(const SpmmParams& p, const int4 it, float4 (&acc)[NCHUNK],
+                                                int lane) {
+  if (it.w < 0) {
+    spmm_epilogue<NCHUNK>(p, it.x, acc, lane);
+  } else {
+    float4* dst = reinterpret_cast<float4*>(p.partial + (size_t)it.w * p.ldp);
+#pragma unroll
+    for (int ch = 0; ch < NCHUNK; ++ch)
+      if (lane + 32 * ch < p.nf4) dst[lane + 32 * ch] = acc[ch];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// variant 0: LDG.128 register gather
+// ---------------------------------------------------------------------------------------
+template <int NCHUNK, int U>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_ldg_kernel(const SpmmParams p) {
+  const int lane = threadIdx.x & 31;
+  const int item = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (item >= p.n_items) return;
+  const int4 it = __ldg(p.items + item);
+  const uint64_t pol = policy_evict_first();
+  float4 acc[NCHUNK];
+#pragma unroll
+  for (int ch = 0; ch < NCHUNK; ++ch) acc[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* Bs = reinterpret_cast<const float4*>(p.B + p.col0) + lane;
+  const size_t ldb4 = (size_t)(p.ldb >> 2);
+
+  for (int base = it.y; base < it.z; base += 32) {
+    const int k = base + lane;
+    int c = 0;
+    float a = 0.f;
+    if (k < it.z) {
+      c = ld_stream_s32(p.col + k, pol);
+      a = ld_stream_f32(p.val + k, pol);
+    }
+    const int cnt = min(32, it.z - base);
+    for (int j = 0; j < cnt; j += U) {
+      float4 x[U][NCHUNK];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int cu = __shfl_sync(0xffffffffu, c, (j + u) & 31);
+        const float4* src = Bs + (size_t)cu * ldb4;
+        const bool live = (j + u) < cnt;
+#pragma unroll
+        for (int ch = 0; ch < NCHUNK; ++ch) {
+          if (live && lane + 32 * ch < p.nf4) x[u][ch] = ld_gather_f4(src + 32 * ch);
+          else x[u][ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float au = __shfl_sync(0xffffffffu, a, (j + u) & 31);
+#pragma unroll
+        for (int ch = 0; ch < NCHUNK; ++ch) {
+          acc[ch].x = fmaf(au, x[u][ch].x, acc[ch].x);
+          acc[ch].y = fmaf(au, x[u][ch].y, acc[ch].y);
+          acc[ch].z = fmaf(au, x[u][ch].z, acc[ch].z);
+          acc[ch].w = fmaf(au, x[u][ch].w, acc[ch].w);
+        }
+      }
+    }
+  }
+  spmm_store_item<NCHUNK>(p, it, acc, lane);
+}
+
+// ---------------------------------------------------------------------------------------
+// variant 1: bulk-copy (TMA engine) staged gather, persistent CTAs
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+constexpr int kBulkGroup = 4;  // gathered rows per mbarrier phase
+
+template <int NCHUNK, int STAGES, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) spmm_bulk_kernel(const SpmmParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t row_bytes = (uint32_t)p.nf4 * 16u;
+  const uint32_t slot_bytes = (row_bytes + 127u) & ~127u;
+  const uint32_t stage_bytes = slot_bytes * kBulkGroup;
+  unsigned char* my_ring = smem + (size_t)warp * STAGES * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)WARPS * STAGES * stage_bytes) + warp * STAGES;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(smem_u32(bars + s), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const uint32_t ring_u32 = smem_u32(my_ring);
+  const uint32_t bars_u32 = smem_u32(bars);
+  const char* Bbytes = reinterpret_cast<const char*>(p.B + p.col0);
+  const size_t ldb_bytes = (size_t)p.ldb * 4;
+
+  const uint64_t pol = policy_evict_first();
+  uint32_t gseq = 0;  // groups issued == groups consumed at item boundaries (ring position)
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(p.counter, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= p.n_items) break;
+    const int4 it = __ldg(p.items + item);
+    const int n = it.z - it.y;
+    const int ngroups = (n + kBulkGroup - 1) / kBulkGroup;
+    float4 acc[NCHUNK];
+#pragma unroll
+    for (int ch = 0; ch < NCHUNK; ++ch) acc[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    int ci = 0;      // column block of the issue side (32 nonzeros)
+    float vc = 0.f;  // value block of the consume side
+    int issued = 0;
+    // issue group g (all lanes execute; lanes < kBulkGroup issue one row copy each)
+    auto issue = [&](int g) {
+      const int k0 = g * kBulkGroup;  // nonzero offset inside the item
+      if ((k0 & 31) == 0) {
+        const int k = it.y + k0 + lane;
+        ci = k < it.z ? ld_stream_s32(p.col + k, pol) : 0;
+      }
+      const int rows = min(kBulkGroup, n - k0);
+      const uint32_t stage = (gseq + (uint32_t)g) % STAGES;
+      const uint32_t bar = bars_u32 + stage * 8u;
+      const int c = __shfl_sync(0xffffffffu, ci, (k0 + lane) & 31);
+      if (lane == 0) mbar_expect_tx(bar, row_bytes * (uint32_t)rows);
+      __syncwarp();
+      if (lane < rows)
+        bulk_g2s(ring_u32 + stage * stage_bytes + (uint32_t)lane * slot_bytes, Bbytes + (size_t)c * ldb_bytes,
+                 row_bytes, bar);
+    };
+    for (; issued < ngroups && issued < STAGES; ++issued) issue(issued);
+
+    for (int g = 0; g < ngroups; ++g) {
+      const int k0 = g * kBulkGroup;
+      if ((k0 & 31) == 0) {
+        const int k = it.y + k0 + lane;
+        vc = k < it.z ? ld_stream_f32(p.val + k, pol) : 0.f;
+      }
+      const uint32_t seq = gseq + (uint32_t)g;
+      const uint32_t stage = seq % STAGES;
+      mbar_wait(bars_u32 + stage * 8u, (seq / STAGES) & 1u);
+      const int rows = min(kBulkGroup, n - k0);
+      const unsigned char* sbase = my_ring + (size_t)stage * stage_bytes;
+#pragma unroll
+      for (int r = 0; r < kBulkGroup; ++r) {
+        if (r < rows) {
+          const float a = __shfl_sync(0xffffffffu, vc, (k0 + r) & 31);
+          const float4* srow = reinterpret_cast<const float4*>(sbase + (size_t)r * slot_bytes);
+#pragma unroll
+          for (int ch = 0; ch < NCHUNK; ++ch) {
+            if (lane + 32 * ch < p.nf4) {
+              const float4 x = srow[lane + 32 * ch];
+              acc[ch].x = fmaf(a, x.x, acc[ch].x);
+              acc[ch].y = fmaf(a, x.y, acc[ch].y);
+              acc[ch].z = fmaf(a, x.z, acc[ch].z);
+              acc[ch].w = fmaf(a, x.w, acc[ch].w);
+            }
+          }
+        }
+      }
+      __syncwarp();  // every lane has read the stage before it is re-armed
+      if (issued < ngroups) {
+        issue(issued);
+        ++issued;
+      }
+    }
+    gseq += (uint32_t)ngroups;
+    spmm_store_item<NCHUNK>(p, it, acc, lane);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// long rows: add the per-item partial sums in item order, then the epilogue
+// ---------------------------------------------------------------------------------------
+template <int NCHUNK>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_fixup_kernel(const SpmmParams p) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (i >= p.n_long) return;
+  const int row = p.long_rows[3 * i], s0 = p.long_rows[3 * i + 1], ns = p.long_rows[3 * i + 2];
+  float4 acc[NCHUNK];
+#pragma unroll
+  for (int ch = 0; ch < NCHUNK; ++ch) acc[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = s0; s < s0 + ns; ++s) {
+    const float4* src = reinterpret_cast<const float4*>(p.partial + (size_t)s * p.ldp);
+#pragma unroll
+    for (int ch = 0; ch < NCHUNK; ++ch) {
+      if (lane + 32 * ch < p.nf4) {
+        const float4 x = src[lane + 32 * ch];
+        acc[ch].x += x.x; acc[ch].y += x.y; acc[ch].z += x.z; acc[ch].w += x.w;
+      }
+    }
+  }
+  spmm_epilogue<NCHUNK>(p, row, acc, lane);
+}
+
+template <int NCHUNK>
+int launch_pass(gcnb_ctx* ctx, const SpmmParams& p) {
+  const int grid = cdiv(p.n_items, kWarpsPerCta);
+  if (p.n_items > 0) {
+    if (ctx->spmm_variant == 1) {
+      constexpr int STAGES = NCHUNK == 4 ? 3 : 4, WARPS = 8;
+      const uint32_t row_bytes = (uint32_t)p.nf4 * 16u;
+      const uint32_t slot_bytes = (row_bytes + 127u) & ~127u;
+      const size_t smem = (size_t)WARPS * STAGES * kBulkGroup * slot_bytes + (size_t)WARPS * STAGES * 8;
+      auto kern = spmm_bulk_kernel<NCHUNK, STAGES, WARPS>;
+      GCNB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      GCNB_CUDA(ctx, cudaMemsetAsync(p.counter, 0, sizeof(int), ctx->stream));
+      int ctas_per_sm = (int)((220u * 1024u) / (smem + 1024));
+      if (ctas_per_sm < 1) ctas_per_sm = 1;
+      if (ctas_per_sm > 4) ctas_per_sm = 4;
+      int g = ctx->sm_count * ctas_per_sm;
+      if (g > grid) g = grid;
+      kern<<<g, WARPS * 32, smem, ctx->stream>>>(p);
+      GCNB_LAUNCHED(ctx);
+    } else {
+      int U = ctx->spmm_unroll;
+      if (U == 0) U = NCHUNK <= 2 ? 8 : 4;
+      if (U >= 8) spmm_ldg_kernel<NCHUNK, 8><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(p);
+      else if (U >= 4) spmm_ldg_kernel<NCHUNK, 4><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(p);
+      else spmm_ldg_kernel<NCHUNK, 2><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(p);
+      GCNB_LAUNCHED(ctx);
+    }
+  }
+  if (p.n_long > 0) {
+    spmm_fixup_kernel<NCHUNK><<<cdiv(p.n_long, kWarpsPerCta), kWarpsPerCta * 32, 0, ctx->stream>>>(p);
+    GCNB_LAUNCHED(ctx);
+  }
+  return GCNB_OK;
+}
+
+constexpr int kMaxPassCols = 512;
+
+}  // namespace
+
+extern "C" size_t gcnb_spmm_workspace_bytes(const gcnb_csr* A, int32_t K) {
+  if (!A) return 0;
+  const int pass_cols = K < kMaxPassCols ? ((K + 3) / 4) * 4 : kMaxPassCols;
+  return 256 + (size_t)A->n_slots * pass_cols * sizeof(float);
+}
+
+extern "C" int gcnb_csr_plan(const int32_t* rowptr, int32_t n_rows, int32_t chunk, int32_t* n_items,
+                             int32_t* n_long, int32_t* n_slots, int32_t* items, int32_t* long_rows) {
+  if (!rowptr || n_rows < 0 || chunk <= 0 || !n_items || !n_long || !n_slots) return GCNB_E_INVALID;
+  long long ni = 0, nl = 0, ns = 0;
+  for (int r = 0; r < n_rows; ++r) {
+    const long long d = (long long)rowptr[r + 1] - rowptr[r];
+    if (d < 0) return GCNB_E_INVALID;
+    const long long pieces = d <= chunk ? 1 : (d + chunk - 1) / chunk;
+    if (pieces > 1) {
+      if (long_rows) {
+        long_rows[3 * nl] = r;
+        long_rows[3 * nl + 1] = (int32_t)ns;
+        long_rows[3 * nl + 2] = (int32_t)pieces;
+      }
+      // even split keeps the pieces of one row the same size
+      const long long per = (d + pieces - 1) / pieces;
+      for (long long q = 0; q < pieces; ++q) {
+        if (items) {
+          const long long b = rowptr[r] + q * per;
+          long long e = b + per;
+          if (e > rowptr[r + 1]) e = rowptr[r + 1];
+          items[4 * ni] = r; items[4 * ni + 1] = (int32_t)b; items[4 * ni + 2] = (int32_t)e;
+          items[4 * ni + 3] = (int32_t)(ns + q);
+        }
+        ++ni;
+      }
+      ns += pieces;
+      ++nl;
+    } else {
+      if (items) {
+        items[4 * ni] = r; items[4 * ni + 1] = rowptr[r]; items[4 * ni + 2] = rowptr[r + 1];
+        items[4 * ni + 3] = -1;
+      }
+      ++ni;
+    }
+    if (ni > 0x7fffffffLL || ns > 0x7fffffffLL) return GCNB_E_UNSUPPORTED;
+  }
+  *n_items = (int32_t)ni; *n_long = (int32_t)nl; *n_slots = (int32_t)ns;
+  return GCNB_OK;
+}
+
+extern "C" int gcnb_spmm_csr_f32(gcnb_ctx* ctx, const gcnb_csr* A, const float* B, int32_t ldb, float* C,
+                                 int32_t ldc, int32_t K, const gcnb_epilogue* epi) {
+  if (!ctx) return GCNB_E_INVALID;
+  GCNB_REQUIRE(ctx, A && B && C, "null matrix");
+  GCNB_REQUIRE(ctx, K > 0, "K must be positive");
+  const int K4 = ((K + 3) / 4) * 4;
+  GCNB_REQUIRE(ctx, (ldb % 4) == 0 && (ldc % 4) == 0 && ldb >= K4 && ldc >= K4, "ldb/ldc: multiple of 4, >= K rounded to 4");
+  GCNB_REQUIRE(ctx, aligned16(B) && aligned16(C), "B and C must be 16-byte aligned");
+  GCNB_REQUIRE(ctx, A->n_rows == 0 || (A->items && A->rowptr), "CSR not planned");
+  GCNB_REQUIRE(ctx, A->nnz == 0 || (A->colidx && A->val), "CSR arrays missing");
+  GCNB_REQUIRE(ctx, A->n_long == 0 || A->long_rows, "long row table missing");
+  if (epi) {
+    GCNB_REQUIRE(ctx, !epi->softmax || K <= kMaxPassCols, "softmax epilogue needs K <= 512");
+    GCNB_REQUIRE(ctx, !epi->bias || aligned16(epi->bias), "bias must be 16-byte aligned");
+    GCNB_REQUIRE(ctx, epi->dropout_p >= 0.f && epi->dropout_p < 1.f, "dropout_p in [0,1)");
+    GCNB_REQUIRE(ctx, !epi->logits || aligned16(epi->logits), "logits must be 16-byte aligned");
+  }
+  if (A->n_rows == 0) return GCNB_OK;
+  const size_t need = gcnb_spmm_workspace_bytes(A, K);
+  if (A->n_slots > 0 || ctx->spmm_variant == 1) {
+    if (!ctx->ws || ctx->ws_bytes < need)
+      return gcnb_fail(ctx, GCNB_E_WORKSPACE, "spmm needs %s%lld workspace bytes, have %lld", "", (long long)need,
+                       (long long)ctx->ws_bytes);
+  }
+  ProfScope scope(ctx, A->tag >= 0 && A->tag < GCNB_NTAGS ? A->tag : GCNB_TAG_SPMM_A);
+  SpmmParams p;
+  memset(&p, 0, sizeof(p));
+  p.items = reinterpret_cast<const int4*>(A->items);
+  p.n_items = A->n_items;
+  p.col = A->colidx;
+  p.val = A->val;
+  p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.K = K;
+  p.counter = reinterpret_cast<int*>(ctx->ws);
+  p.partial = ctx->ws ? reinterpret_cast<float*>(reinterpret_cast<char*>(ctx->ws) + 256) : nullptr;
+  p.long_rows = A->long_rows;
+  p.n_long = A->n_long;
+  if (epi) {
+    p.bias = epi->bias; p.act = epi->act; p.softmax = epi->softmax; p.accumulate = epi->accumulate;
+    if (epi->dropout_p > 0.f) {
+      p.thresh = dropout_threshold(epi->dropout_p);
+      if (p.thresh == 0u) p.thresh = 1u;
+      p.scale = 1.f / (1.f - epi->dropout_p);
+    }
+    p.seed = epi->seed; p.row0 = epi->row0; p.logits = epi->logits;
+  }
+  for (int c0 = 0; c0 < K4; c0 += kMaxPassCols) {
+    const int w = (K4 - c0) < kMaxPassCols ? (K4 - c0) : kMaxPassCols;
+    p.col0 = c0;
+    p.nf4 = w / 4;
+    p.ldp = w;
+    const int nchunk = (p.nf4 + 31) / 32;
+    int rc;
+    switch (nchunk) {
+      case 1: rc = launch_pass<1>(ctx, p); break;
+      case 2: rc = launch_pass<2>(ctx, p); break;
+      case 3: rc = launch_pass<3>(ctx, p); break;
+      default: rc = launch_pass<4>(ctx, p); break;
+    }
+    if (rc != GCNB_OK) return rc;
+  }
+  return GCNB_OK;
+}

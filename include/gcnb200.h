@@ -1,0 +1,201 @@
+/* gcnb200.h -- C ABI of libgcnb200.so: the B200 (sm_100a) kernels behind geographconv's GCN
+ * hot path.  This is the drop-in boundary: the reference has no FFI of its own
+ * (it is pure Python on Theano/Lasagne), so the entry points below are the operations its
+ * gcnmodel.py asks Theano for, one function per op, each citing the reference call site it
+ * replaces.  geographconv_b200/gcnmodel.py binds them with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / numpy types.
+ *  - every `const float*` / `float*` matrix is DEVICE memory, row-major fp32, with a leading
+ *    dimension (`ld*`, in floats) that is a multiple of 4 and >= the logical width rounded up
+ *    to 4; base pointers are 16-byte aligned.  Padding columns hold zeros and kernels keep them
+ *    zero.  Index arrays are int32 (gcnmain.py:167-168, gcnmodel.py:329).
+ *  - the CALLER owns all device memory (allocated with any allocator; the Python host uses
+ *    torch as the HBM allocator).  The library never allocates or frees device memory; scratch
+ *    is a caller-provided workspace (gcnb_set_workspace).
+ *  - all ops are asynchronous on the context's stream; only gcnb_sync / gcnb_prof_collect /
+ *    the *_sync helpers block the host.
+ *  - return value: 0 (GCNB_OK) or a negative gcnb_status; gcnb_last_error(ctx) explains.
+ *  - one host thread per context (the reference is single-threaded, gcnmodel.py:429-430).
+ */
+#ifndef GCNB200_H
+#define GCNB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCNB_VERSION 100
+
+typedef struct gcnb_ctx gcnb_ctx;
+
+enum gcnb_status {
+  GCNB_OK = 0,
+  GCNB_E_INVALID = -1,     /* bad argument (shape, alignment, null pointer) */
+  GCNB_E_CUDA = -2,        /* a CUDA runtime / driver call failed */
+  GCNB_E_WORKSPACE = -3,   /* workspace missing or too small */
+  GCNB_E_UNSUPPORTED = -4  /* shape outside what the kernels are instantiated for */
+};
+
+/* lasagne.nonlinearities used by gcnmodel.py: tanh (:347, live), rectify (:345, commented
+ * out), sigmoid (:286 gate), linear (:188). */
+enum gcnb_act { GCNB_ACT_LINEAR = 0, GCNB_ACT_TANH = 1, GCNB_ACT_RELU = 2, GCNB_ACT_SIGMOID = 3 };
+
+/* profiling classes: the step-time split SURVEY.md 8d asks for */
+enum gcnb_tag {
+  GCNB_TAG_SPMM_A = 0,  /* A_hat . H     (structured_dot(A, .), gcnmodel.py:130,153) */
+  GCNB_TAG_SPMM_X = 1,  /* X . W0        (structured_dot(input, W), gcnmodel.py:39) */
+  GCNB_TAG_SPMM_XT = 2, /* X^T . dz      (grad of gcnmodel.py:39 wrt W) */
+  GCNB_TAG_GEMM = 3,    /* T.dot         (gcnmodel.py:126,149,285) and its grads */
+  GCNB_TAG_ELEM = 4,    /* bias / activation / gate / dropout element-wise work */
+  GCNB_TAG_LOSS = 5,    /* softmax cross-entropy, argmax, gathers (gcnmodel.py:376-389) */
+  GCNB_TAG_ADAM = 6,    /* lasagne.updates.adam (gcnmodel.py:407) */
+  GCNB_TAG_COPY = 7,    /* host<->device copies issued through this ABI */
+  GCNB_NTAGS = 8
+};
+
+/* ---------------------------------------------------------------- context ------------- */
+int gcnb_version(void);
+/* `stream` is a cudaStream_t (NULL = create a private non-blocking stream). */
+int gcnb_create(int device, void* stream, gcnb_ctx** out);
+int gcnb_destroy(gcnb_ctx* ctx);
+const char* gcnb_last_error(const gcnb_ctx* ctx);
+int gcnb_set_stream(gcnb_ctx* ctx, void* stream);
+void* gcnb_get_stream(const gcnb_ctx* ctx);
+int gcnb_set_workspace(gcnb_ctx* ctx, void* dev_ptr, size_t bytes);
+/* named integer options: "spmm_variant" (0 = LDG.128 register gather, 1 = bulk-copy/TMA staged),
+ * "spmm_unroll" (nonzeros gathered per batch), "gemm_tc" (1 = tcgen05 path where supported). */
+int gcnb_set_option(gcnb_ctx* ctx, const char* name, int value);
+int gcnb_get_option(const gcnb_ctx* ctx, const char* name, int* value);
+int gcnb_sync(gcnb_ctx* ctx);
+int gcnb_sm_count(const gcnb_ctx* ctx);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+long long gcnb_launch_count(const gcnb_ctx* ctx);
+/* per-tag CUDA-event timing of every op, recorded on the context's stream */
+int gcnb_prof_enable(gcnb_ctx* ctx, int on);
+int gcnb_prof_reset(gcnb_ctx* ctx);
+/* synchronises the stream; fills ms[GCNB_NTAGS] and ops[GCNB_NTAGS] (accumulated since reset) */
+int gcnb_prof_collect(gcnb_ctx* ctx, float* ms, long long* ops);
+
+/* ---------------------------------------------------------------- transfers ----------- */
+int gcnb_h2d(gcnb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int gcnb_d2h(gcnb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+int gcnb_memset(gcnb_ctx* ctx, void* dst_dev, int byte, size_t bytes);
+
+/* ---------------------------------------------------------------- CSR ----------------- */
+/* A CSR matrix resident in device memory plus its work decomposition ("plan"): every row is
+ * cut into items of at most `chunk` nonzeros; a row that needs more than one item is a "long"
+ * row whose items write partial sums that a fix-up pass adds in order (deterministic).
+ * Replaces the scipy CSR that theano.sparse.csr_matrix inputs carry (gcnmodel.py:338,342). */
+typedef struct gcnb_csr {
+  int32_t n_rows;
+  int32_t n_cols;
+  int64_t nnz;
+  const int32_t* rowptr; /* device, n_rows + 1 */
+  const int32_t* colidx; /* device, nnz */
+  const float* val;      /* device, nnz */
+  const int32_t* items;  /* device, 4 * n_items: {row, begin, end, slot (-1 = direct)} */
+  int32_t n_items;
+  const int32_t* long_rows; /* device, 3 * n_long: {row, first_slot, n_slots_of_row} */
+  int32_t n_long;
+  int32_t n_slots;
+  int32_t tag; /* gcnb_tag the SpMM time is booked under */
+} gcnb_csr;
+
+/* Host-side planning over a HOST rowptr.  Call once with items == NULL to get the counts, then
+ * again with host buffers of 4*n_items and 3*n_long int32 to fill. */
+int gcnb_csr_plan(const int32_t* host_rowptr, int32_t n_rows, int32_t chunk, int32_t* n_items,
+                  int32_t* n_long, int32_t* n_slots, int32_t* items, int32_t* long_rows);
+
+/* fused epilogue of the SpMM: out = dropout(act(acc + bias)) or softmax(acc + bias);
+ * C = out, or C += out when `accumulate`. */
+typedef struct gcnb_epilogue {
+  const float* bias;   /* device, K floats padded to a multiple of 4 with zeros; or NULL */
+  int32_t act;         /* gcnb_act */
+  int32_t softmax;     /* 1: row softmax over the K columns after the bias (K <= 512) */
+  int32_t accumulate;  /* 1: C += out */
+  float dropout_p;     /* 0: none.  Inverted dropout, scale 1/(1-p) (lasagne DropoutLayer) */
+  uint64_t seed;       /* Philox key */
+  int64_t row0;        /* global index of local row 0 (row-partitioned runs draw the same mask) */
+  float* logits;       /* optional (softmax only): pre-softmax values, same ld as C; or NULL */
+} gcnb_epilogue;
+
+/* C[n_rows x K] = epilogue( A[n_rows x n_cols] . B[n_cols x K] )
+ * theano.sparse.structured_dot: gcnmodel.py:39 (X.W0), :130 (A.(xW)), :153 (output layer) and
+ * its gradient structured_dot(a.T, g).  `epi` may be NULL (plain product). */
+int gcnb_spmm_csr_f32(gcnb_ctx* ctx, const gcnb_csr* A, const float* B, int32_t ldb, float* C,
+                      int32_t ldc, int32_t K, const gcnb_epilogue* epi);
+/* workspace bytes the call above needs for this matrix and K */
+size_t gcnb_spmm_workspace_bytes(const gcnb_csr* A, int32_t K);
+
+/* ---------------------------------------------------------------- dense --------------- */
+/* C[M x N] = act(op(A) . op(B) + bias), or C += op(A).op(B) when accumulate (bias/act then
+ * unused).  op(A) is M x K: transA == 0 -> A is M x K row-major (lda), else A is K x M.
+ * T.dot: gcnmodel.py:126,149,215 and the dgrad / wgrad products of its gradient. */
+int gcnb_gemm_f32(gcnb_ctx* ctx, int32_t transA, int32_t transB, int32_t M, int32_t N, int32_t K,
+                  const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc,
+                  int32_t accumulate, const float* bias, int32_t act);
+size_t gcnb_gemm_workspace_bytes(int32_t transA, int32_t M, int32_t N, int32_t K);
+
+/* The fused highway layer (north-star op):  h = act(S.Wh + bh), t = sigmoid(X.Wt + bt),
+ * Y = t*h + (1-t)*X, with S = A_hat.X computed beforehand by gcnb_spmm_csr_f32.
+ * highway_dense + MultiplicativeGatingLayer: gcnmodel.py:266,281-288.  Wh/Wt are (in, out)
+ * row-major like Lasagne's DenseLayer.W.  H and T (saved for backward) may be NULL. */
+int gcnb_highway_fwd_f32(gcnb_ctx* ctx, int32_t n_rows, int32_t hd, const float* S, int32_t lds,
+                         const float* X, int32_t ldx, const float* Wh, int32_t ldwh,
+                         const float* bh, const float* Wt, int32_t ldwt, const float* bt,
+                         int32_t act, float* Y, int32_t ldy, float* H, int32_t ldh, float* T,
+                         int32_t ldt);
+size_t gcnb_highway_workspace_bytes(int32_t n_rows, int32_t hd);
+
+/* backward of the gate mix: dHpre = dY*T*act'(H), dTpre = dY*(H-X)*T*(1-T), dX = dY*(1-T) */
+int gcnb_highway_bwd_f32(gcnb_ctx* ctx, int32_t n_rows, int32_t hd, int32_t ld, const float* dY,
+                         const float* X, const float* H, const float* T, int32_t act,
+                         float* dHpre, float* dTpre, float* dX);
+
+/* dZ = dY * keep*scale * act'(a), where Yact holds dropout(act(z)) (first layer,
+ * gcnmodel.py:353-357) or act(z) when dropout_p == 0.  In-place (dZ == dY) allowed. */
+int gcnb_act_bwd_f32(gcnb_ctx* ctx, int32_t n_rows, int32_t k, int32_t ld, const float* dY,
+                     const float* Yact, int32_t act, float dropout_p, uint64_t seed, int64_t row0,
+                     float* dZ);
+
+/* out[k] (+)= sum over rows of A[:, k]  (bias gradients).  Deterministic. */
+int gcnb_colsum_f32(gcnb_ctx* ctx, int32_t n_rows, int32_t k, const float* A, int32_t lda,
+                    float* out, int32_t accumulate);
+size_t gcnb_colsum_workspace_bytes(int32_t n_rows, int32_t k);
+
+/* ---------------------------------------------------------------- loss / outputs ------ */
+/* metrics[0] += sum_i -log P[idx[i], labels[i]];  metrics[1] += #(argmax P[idx[i]] == labels[i])
+ * categorical_crossentropy + argmax/eq: gcnmodel.py:376-389. */
+int gcnb_xent_metrics_f32(gcnb_ctx* ctx, const float* P, int32_t ldp, int32_t n_classes,
+                          const int32_t* idx, const int32_t* labels, int32_t n_idx,
+                          float* metrics);
+/* G = 0; G[idx[i], :] += (P[idx[i], :] - onehot(labels[i])) * inv_n   (d mean-CE / d logits) */
+int gcnb_xent_grad_f32(gcnb_ctx* ctx, const float* P, int32_t ldp, int32_t n_classes,
+                       int32_t n_rows, const int32_t* idx, const int32_t* labels, int32_t n_idx,
+                       float inv_n, float* G, int32_t ldg);
+/* preds[i] = argmax P[idx[i], :] (int64), probs[i, :] = P[idx[i], :] packed n_idx x n_classes
+ * f_val outputs: gcnmodel.py:393-394,411. */
+int gcnb_gather_argmax_f32(gcnb_ctx* ctx, const float* P, int32_t ldp, int32_t n_classes,
+                           const int32_t* idx, int32_t n_idx, int64_t* preds, float* probs);
+
+/* ---------------------------------------------------------------- optimiser ----------- */
+/* G += coef*(sign(W) + 2W); reg_sum[0] += sum(|W| + W^2)   (gcnmodel.py:383-387) */
+int gcnb_l1l2_f32(gcnb_ctx* ctx, const float* W, float* G, int64_t n, float coef, float* reg_sum);
+/* One lasagne.updates.adam step (gcnmodel.py:407) over a flat parameter buffer.
+ * state (device, 2 floats) = {t, a_t}; t is incremented on the device. */
+int gcnb_adam_f32(gcnb_ctx* ctx, float* params, const float* grads, float* m, float* v, int64_t n,
+                  float* state, float lr, float beta1, float beta2, float eps);
+
+/* ---------------------------------------------------------------- dropout mask -------- */
+/* materialise the keep mask the fused epilogue draws (tests feed it to the CPU oracle) */
+int gcnb_dropout_mask_u8(gcnb_ctx* ctx, int32_t n_rows, int32_t k, float p, uint64_t seed,
+                         int64_t row0, uint8_t* mask);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCNB200_H */
