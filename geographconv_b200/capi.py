@@ -14,8 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libgcnb200.so")
 
 OK, E_INVALID, E_CUDA, E_WORKSPACE, E_UNSUPPORTED = 0, -1, -2, -3, -4
 ACT = {"linear": 0, "tanh": 1, "relu": 2, "rectify": 2, "sigmoid": 3}
-TAGS = ["spmm_a", "spmm_x", "spmm_xt", "gemm", "elementwise", "loss", "adam", "copy"]
-TAG_SPMM_A, TAG_SPMM_X, TAG_SPMM_XT = 0, 1, 2
+TAGS = ["spmm_a", "spmm_x", "spmm_xt", "gemm", "elementwise", "loss", "adam", "copy", "spmm_a_narrow"]
+TAG_SPMM_A, TAG_SPMM_X, TAG_SPMM_XT, TAG_SPMM_A_NARROW = 0, 1, 2, 8
 
 
 class GcnbError(RuntimeError):

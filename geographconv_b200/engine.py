@@ -1,0 +1,619 @@
+"""Device engine of the GCN hot path: owns the HBM buffers and sequences the C-ABI kernels.
+
+This is the host side of ``f_train`` / ``f_val`` / ``f_gates`` (reference gcnmodel.py:396-411):
+one full-graph forward (+ backward + Adam) per call, all on one CUDA stream, through
+``libgcnb200.so`` only.  PyTorch is the HBM allocator and the NCCL plumbing; there is no
+torch.sparse, no torch.matmul and no CPU fallback anywhere on this path.
+
+Data layout in HBM:
+* every dense matrix is row-major fp32 with leading dimension round_up(cols, 32) floats, so
+  each row starts on a 128-byte line; padding columns are zero and stay zero;
+* weights, gradients and the two Adam moments are four flat buffers with one shared layout
+  (``partition.ParamLayout``, Lasagne ``get_all_param_values`` order);
+* sparse operands are CSR (int32 rowptr / colidx, fp32 val) plus the row-item plan the SpMM
+  kernel walks; X is kept in both CSR (forward X.W0) and transposed CSR (backward X^T.dz).
+
+Layer arithmetic, per SURVEY.md 8a:
+* first layer      H0 = dropout(act(X.W0 + b0))                        (gcnmodel.py:39-42,357)
+* highway layer    S = A.x ; h = act(S.Wh + bh) ; t = sigmoid(x.Wt + bt) ; y = t*h + (1-t)*x
+                   (gcnmodel.py:126-136,266,281-288; (A.x).Wh == A.(x.Wh) by associativity,
+                   the bias is added after both, as in the reference)
+* plain layer      y = act(A.(x.W) + b)                                (gcnmodel.py:372)
+* output layer     P = softmax(A.(x.Wout) + bout)                      (gcnmodel.py:149-157)
+
+Row-partitioned runs (world > 1): rank p owns the contiguous row block
+[p*n_pad, (p+1)*n_pad) of A, X and every activation; before each A-SpMM the dense operand is
+all-gathered (NCCL over NVLink), weight gradients are all-reduced once per step.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from . import capi
+from .capi import ACT, GcnbCsr, GcnbEpilogue
+from .partition import ParamLayout, ld_of, local_index_split, row_blocks, slice_rows, transpose_csr, is_symmetric
+
+SPMM_CHUNK_DEFAULT = 256  # nonzeros per row item (rows longer than this are split; see gcnb_csr_plan)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _pinned(arr):
+    """Copy a host array into page-locked memory (async H2D needs it); returns the ndarray view."""
+    arr = np.ascontiguousarray(arr)
+    if arr.size == 0:
+        return arr
+    t = torch.from_numpy(arr)
+    try:
+        return t.pin_memory().numpy()
+    except RuntimeError:  # no CUDA runtime (CPU-only host): plain memory still works for staging
+        return arr
+
+
+class HostCsr:
+    """Host-side CSR of one SpMM operand: int32 / fp32 arrays in pinned memory plus the row-item plan."""
+
+    def __init__(self, M, chunk):
+        M = M.tocsr()
+        if not M.has_sorted_indices:
+            M = M.copy()
+            M.sort_indices()
+        if M.shape[0] >= 2**31 or M.shape[1] >= 2**31 or M.nnz >= 2**31:
+            raise ValueError("CSR dimensions / nnz per shard must fit int32")
+        self.shape = tuple(int(x) for x in M.shape)
+        self.nnz = int(M.nnz)
+        rowptr = np.ascontiguousarray(M.indptr, dtype=np.int32)
+        items, long_rows, n_slots = capi.csr_plan(rowptr, int(chunk))
+        self.rowptr = _pinned(rowptr)
+        self.colidx = _pinned(np.ascontiguousarray(M.indices, dtype=np.int32))
+        self.val = _pinned(np.ascontiguousarray(M.data, dtype=np.float32))
+        self.items = _pinned(items.reshape(-1))
+        self.long_rows = _pinned(long_rows.reshape(-1))
+        self.n_items, self.n_long, self.n_slots = len(items), len(long_rows), int(n_slots)
+        self.nbytes = sum(a.nbytes for a in (self.rowptr, self.colidx, self.val, self.items, self.long_rows))
+
+
+class HostGraph:
+    """Everything ``Engine.bind`` uploads for one (X, A) pair and one rank: the row block of X and A,
+    the transposed block of X for the backward pass, and A^T's block when A is not symmetric.
+    Built once per (X, A) (the analogue of the reference's preprocess_data output staying in host
+    memory across epochs, gcnmain.py:172-179) and cached by the engine."""
+
+    def __init__(self, X, A, world, rank, chunk, need_backward, assume_symmetric=None):
+        n = X.shape[0]
+        self.n = n
+        self.n_pad, blocks = row_blocks(n, world)
+        self.r0, self.r1 = blocks[rank]
+        self.n_loc = self.r1 - self.r0
+        self.n_tot = self.n_pad * world if world > 1 else n
+        self.need_backward = bool(need_backward)
+
+        def widen(M):  # gathered operands have n_pad*world rows
+            if world > 1 and self.n_tot != n:
+                return sp.csr_matrix((M.data, M.indices, M.indptr), shape=(M.shape[0], self.n_tot))
+            return M
+
+        if world > 1:
+            Xl, Al = slice_rows(X, self.r0, self.r1), widen(slice_rows(A, self.r0, self.r1))
+        else:
+            Xl, Al = X.tocsr(), A.tocsr()
+        self.X = HostCsr(Xl, chunk)
+        self.A = HostCsr(Al, chunk)
+        self.XT = self.AT = None
+        self.symmetric = True
+        if need_backward:
+            self.XT = HostCsr(transpose_csr(Xl), chunk)
+            self.symmetric = bool(is_symmetric(A) if assume_symmetric is None else assume_symmetric)
+            if not self.symmetric:
+                # A^T.G for a row block needs rows r0:r1 of A^T
+                AT = transpose_csr(A)
+                self.AT = HostCsr(widen(slice_rows(AT, self.r0, self.r1)) if world > 1 else AT, chunk)
+        self.nbytes = sum(c.nbytes for c in (self.X, self.A, self.XT, self.AT) if c is not None)
+
+
+class DeviceCsr:
+    """A CSR matrix resident in HBM together with its SpMM work plan (gcnb_csr)."""
+
+    def __init__(self, eng, host: HostCsr, tag):
+        self.shape = host.shape
+        self.nnz = host.nnz
+        self.n_items, self.n_long = host.n_items, host.n_long
+        i32 = lambda n: torch.empty(max(n, 1), dtype=torch.int32, device=eng.dev)
+        self.t_rowptr = i32(host.rowptr.size)
+        self.t_colidx = i32(host.colidx.size)
+        self.t_val = torch.empty(max(host.val.size, 1), dtype=torch.float32, device=eng.dev)
+        self.t_items = i32(host.items.size)
+        self.t_long = i32(host.long_rows.size)
+        s = GcnbCsr()
+        s.n_rows, s.n_cols, s.nnz = host.shape[0], host.shape[1], host.nnz
+        s.rowptr, s.colidx, s.val = self.t_rowptr.data_ptr(), self.t_colidx.data_ptr(), self.t_val.data_ptr()
+        s.items, s.n_items = self.t_items.data_ptr(), host.n_items
+        s.long_rows = self.t_long.data_ptr() if host.n_long else None
+        s.n_long, s.n_slots, s.tag = host.n_long, host.n_slots, int(tag)
+        self.struct = s
+        self.refill(eng, host)
+
+    def refill(self, eng, host):
+        """(Re-)copy the host arrays into the existing device buffers: async H2D on the engine stream."""
+        for dst, src in ((self.t_rowptr, host.rowptr), (self.t_colidx, host.colidx), (self.t_val, host.val),
+                         (self.t_items, host.items), (self.t_long, host.long_rows)):
+            if src.size:
+                eng.ctx.call("gcnb_h2d", _ptr(dst), C.c_void_p(src.ctypes.data), src.nbytes)
+
+    def retagged(self, tag):
+        """Same device arrays booked under another profiling tag."""
+        import copy
+        other = copy.copy(self)
+        s = GcnbCsr()
+        C.memmove(C.byref(s), C.byref(self.struct), C.sizeof(GcnbCsr))
+        s.tag = int(tag)
+        other.struct = s
+        return other
+
+    def touched_bytes(self, K):
+        """SURVEY.md 8d B_touch: nnz*(4+4) + (rows+1)*4 + nnz*K*4 + rows*K*4."""
+        return self.nnz * 8 + (self.shape[0] + 1) * 4 + self.nnz * K * 4 + self.shape[0] * K * 4
+
+
+class Engine:
+    """One GPU's share of the GCN: weights (replicated), row block of the graph, activations."""
+
+    def __init__(self, layout: ParamLayout, drop_out=0.0, regul_coef=0.0, nonlin="tanh", device=None,
+                 group=None, spmm_chunk=SPMM_CHUNK_DEFAULT, keep_logits=False):
+        if not torch.cuda.is_available():
+            raise capi.GcnbError("geographconv_b200 needs a B200 GPU: torch.cuda.is_available() is False "
+                                 "(there is no CPU fallback)")
+        self.layout = layout
+        self.drop_out = float(drop_out)
+        self.regul_coef = float(regul_coef)
+        self.act = ACT[nonlin]
+        self.spmm_chunk = int(spmm_chunk)
+        self.keep_logits = keep_logits
+        self.group = group
+        self.world = torch.distributed.get_world_size(group) if group is not None else 1
+        self.rank = torch.distributed.get_rank(group) if group is not None else 0
+        if device is None:
+            device = torch.cuda.current_device()
+        self.dev = torch.device("cuda", int(device))
+        torch.cuda.set_device(self.dev)
+        self.stream = torch.cuda.current_stream(self.dev)
+        self.ctx = capi.Context(int(device), C.c_void_p(self.stream.cuda_stream))
+        self.lib = self.ctx.lib
+        L = layout
+        self.params = torch.zeros(L.total, dtype=torch.float32, device=self.dev)
+        self.grads = torch.zeros(L.total, dtype=torch.float32, device=self.dev)
+        self.adam_m = torch.zeros(L.total, dtype=torch.float32, device=self.dev)
+        self.adam_v = torch.zeros(L.total, dtype=torch.float32, device=self.dev)
+        self.adam_state = torch.zeros(2, dtype=torch.float32, device=self.dev)
+        # metrics: train {loss_sum, n_correct}, dev {loss_sum, n_correct}, reg_sum, pad
+        self.metrics = torch.zeros(8, dtype=torch.float32, device=self.dev)
+        self.metrics_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self.ws = None
+        self._keepalive = []
+        self.n = None  # rows bound (global)
+        self.A = self.X = self.XT = self.AT = None
+        self._bound_key = None
+        self.host = None
+        self._idx_cache = {}
+        self.h2d_bytes_last_bind = 0
+        self.step_count = 0
+
+    # ------------------------------------------------------------------ small helpers
+    def upload(self, arr):
+        """Host ndarray -> fresh device tensor through gcnb_h2d (async on the engine stream)."""
+        arr = np.ascontiguousarray(arr)
+        if arr.dtype == np.float32:
+            t = torch.empty(arr.size, dtype=torch.float32, device=self.dev)
+        elif arr.dtype == np.int32:
+            t = torch.empty(arr.size, dtype=torch.int32, device=self.dev)
+        elif arr.dtype == np.uint8:
+            t = torch.empty(arr.size, dtype=torch.uint8, device=self.dev)
+        else:
+            raise TypeError(arr.dtype)
+        if arr.size:
+            self.ctx.call("gcnb_h2d", _ptr(t), C.c_void_p(arr.ctypes.data), arr.nbytes)
+            # pageable sources are staged by the driver before cudaMemcpyAsync returns; pinned
+            # sources must outlive the copy -- keep a reference until the next sync
+            self._keepalive.append(arr)
+        return t
+
+    def _ensure_ws(self, nbytes):
+        nbytes = int(nbytes)
+        if self.ws is None or self.ws.numel() < nbytes:
+            self.ctx.sync()
+            self.ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=self.dev)
+            self.ctx.call("gcnb_set_workspace", _ptr(self.ws), self.ws.numel())
+
+    def _pptr(self, name):
+        e = self.layout.by_name[name]
+        return C.c_void_p(self.params.data_ptr() + 4 * e["offset"]), e["ld"]
+
+    def _gptr(self, name):
+        e = self.layout.by_name[name]
+        return C.c_void_p(self.grads.data_ptr() + 4 * e["offset"]), e["ld"]
+
+    def _zeros(self, rows, ld):
+        return torch.zeros((max(rows, 1), ld), dtype=torch.float32, device=self.dev)
+
+    # ------------------------------------------------------------------ parameters
+    def set_params(self, params):
+        flat = self.layout.pack(params)
+        self.ctx.call("gcnb_h2d", _ptr(self.params), C.c_void_p(flat.ctypes.data), flat.nbytes)
+        self.ctx.sync()
+
+    def get_params(self):
+        flat = np.empty(self.layout.total, dtype=np.float32)
+        self.ctx.call("gcnb_d2h", C.c_void_p(flat.ctypes.data), _ptr(self.params), flat.nbytes)
+        self.ctx.sync()
+        return self.layout.unpack(flat)
+
+    def get_grads(self):
+        flat = np.empty(self.layout.total, dtype=np.float32)
+        self.ctx.call("gcnb_d2h", C.c_void_p(flat.ctypes.data), _ptr(self.grads), flat.nbytes)
+        self.ctx.sync()
+        return self.layout.unpack(flat)
+
+    # ------------------------------------------------------------------ graph / features
+    def bind(self, X, A, need_backward=True, force_upload=False, assume_symmetric=None):
+        """Make CSR ``X`` (N x F) and ``A`` (N x N) resident (row block of this rank) and size buffers.
+
+        The reference passes host SciPy matrices on every f_train / f_val call
+        (gcnmain.py:221,226,231).  Host preparation (row block, transpose, plan, pinned copy) and
+        the device copies are cached on object identity + (shape, nnz): only the first call pays
+        for them.  ``force_upload`` repeats the host->device copies (bench.py's end-to-end leg).
+        """
+        if not sp.issparse(X) or not sp.issparse(A):
+            raise ValueError("Input for this layer must be sparse")  # gcnmodel.py:34-36
+        key = (id(X), X.shape, X.nnz, id(A), A.shape, A.nnz)
+        same = self._bound_key == key and (self.host.need_backward or not need_backward)
+        if same and not force_upload:
+            return
+        if not same:
+            if X.shape[1] != self.layout.input_size:
+                raise ValueError("X has %d columns, model input_size is %d" % (X.shape[1], self.layout.input_size))
+            if A.shape[0] != A.shape[1] or A.shape[0] != X.shape[0]:
+                raise ValueError("A must be N x N with N = X.shape[0]")
+            self.ctx.sync()
+            hg = HostGraph(X, A, self.world, self.rank, self.spmm_chunk, need_backward, assume_symmetric)
+            self.host = hg
+            self.n, self.n_pad, self.r0, self.r1 = hg.n, hg.n_pad, hg.r0, hg.r1
+            self.n_loc, self.n_tot, self.symmetric = hg.n_loc, hg.n_tot, hg.symmetric
+            self.X = DeviceCsr(self, hg.X, capi.TAG_SPMM_X)
+            self.A = DeviceCsr(self, hg.A, capi.TAG_SPMM_A)
+            self.XT = DeviceCsr(self, hg.XT, capi.TAG_SPMM_XT) if hg.XT is not None else None
+            self.AT = DeviceCsr(self, hg.AT, capi.TAG_SPMM_A) if hg.AT is not None else None
+            self._alloc_buffers(need_backward)
+            self._bound_key = key
+            self._idx_cache = {}
+        else:
+            hg = self.host
+            for d, h in ((self.X, hg.X), (self.A, hg.A), (self.XT, hg.XT), (self.AT, hg.AT)):
+                if d is not None:
+                    d.refill(self, h)
+        self.A_out = self.A.retagged(capi.TAG_SPMM_A_NARROW)
+        self.AT_out = self.AT.retagged(capi.TAG_SPMM_A_NARROW) if self.AT is not None else None
+        self.h2d_bytes_last_bind = hg.nbytes
+
+    def _alloc_buffers(self, need_backward):
+        L = self.layout
+        n = self.n_pad if self.world > 1 else self.n_loc
+        hd = L.hid[0]
+        widths = [hd] + [l["n_out"] for l in L.layers]
+        self.ldh = [ld_of(w) for w in widths]
+        self.ldc = ld_of(L.output_size)
+        self.nbuf = n
+        self.H0 = self._zeros(n, self.ldh[0])
+        self.lay = []
+        for i, l in enumerate(L.layers):
+            b = {"Y": self._zeros(n, self.ldh[i + 1])}
+            if l["kind"] == "hw":
+                b["H"] = self._zeros(n, self.ldh[i + 1])
+                b["T"] = self._zeros(n, self.ldh[i + 1])
+            self.lay.append(b)
+        maxld = max(self.ldh + [self.ldc])
+        self.S = self._zeros(n, maxld)  # A.x scratch (highway) / x.W scratch (plain, output)
+        self.P = self._zeros(n, self.ldc)
+        self.logits = self._zeros(n, self.ldc) if self.keep_logits else None
+        self.gath = self._zeros(self.n_tot, maxld) if self.world > 1 else None
+        if need_backward:
+            self.G = self._zeros(n, self.ldc)
+            self.U = self._zeros(n, maxld)
+            self.dX = self._zeros(n, maxld)
+            self.dH = self._zeros(n, maxld)
+            self.dT = self._zeros(n, maxld)
+        # workspace: the largest scratch any op of the step needs
+        need = 1 << 20
+        need = max(need, self.lib.gcnb_spmm_workspace_bytes(C.byref(self.A.struct), max(widths + [L.output_size])))
+        need = max(need, self.lib.gcnb_spmm_workspace_bytes(C.byref(self.X.struct), hd))
+        need = max(need, self.lib.gcnb_highway_workspace_bytes(0, max(widths)))
+        if need_backward:
+            need = max(need, self.lib.gcnb_spmm_workspace_bytes(C.byref(self.XT.struct), hd))
+            if self.AT is not None:
+                need = max(need, self.lib.gcnb_spmm_workspace_bytes(C.byref(self.AT.struct),
+                                                                    max(widths + [L.output_size])))
+            wmax = max(widths + [L.output_size])
+            need = max(need, self.lib.gcnb_gemm_workspace_bytes(1, wmax, wmax, max(n, 1)))
+            need = max(need, self.lib.gcnb_colsum_workspace_bytes(n, wmax))
+        self._ensure_ws(need)
+
+    def index_arrays(self, idx, labels=None, force_upload=False):
+        """Global node indices (+ their labels, aligned with ``idx``) -> device int32 arrays of this
+        rank's local rows.  Cached on the host arrays' identity and content."""
+        idx = np.asarray(idx)
+        if labels is not None:
+            labels = np.asarray(labels)
+            if len(labels) != len(idx):
+                raise AssertionError("inputs and targets differ in length")  # gcnmodel.py:304
+        key = (idx.ctypes.data, idx.shape, None if labels is None else labels.ctypes.data)
+        hit = self._idx_cache.get(key)
+        if hit is not None and np.array_equal(hit[3], idx):
+            if force_upload:
+                for dst, src in ((hit[0], hit[4]), (hit[1], hit[5])):
+                    if dst is not None and src.size:
+                        self.ctx.call("gcnb_h2d", _ptr(dst), C.c_void_p(src.ctypes.data), src.nbytes)
+            return hit[0], hit[1], hit[2]
+        have_labels = labels is not None
+        if labels is None:
+            labels = np.zeros(len(idx), np.int32)
+        if self.world > 1:
+            li, ll = local_index_split(idx, labels, self.r0, self.r1)
+        else:
+            li, ll = idx.astype(np.int32), np.asarray(labels).astype(np.int32)
+        li, ll = _pinned(li), _pinned(ll)
+        d_idx = self.upload(li)
+        d_lab = self.upload(ll) if have_labels else None
+        self.ctx.sync()
+        self._keepalive = []
+        self._idx_cache[key] = (d_idx, d_lab, len(li), idx.copy(), li, ll)
+        return d_idx, d_lab, len(li)
+
+    # ------------------------------------------------------------------ ops
+    def _spmm(self, csr, B, ldb, Cbuf, ldc, K, bias=None, act=0, softmax=0, accumulate=0, dropout_p=0.0,
+              seed=0, logits=None):
+        epi = GcnbEpilogue()
+        epi.bias = bias.value if isinstance(bias, C.c_void_p) else bias
+        epi.act, epi.softmax, epi.accumulate = int(act), int(softmax), int(accumulate)
+        epi.dropout_p, epi.seed, epi.row0 = float(dropout_p), int(seed) & (2**64 - 1), int(self.r0)
+        epi.logits = logits.data_ptr() if logits is not None else None
+        Bp = B if isinstance(B, C.c_void_p) else _ptr(B)
+        Cp = Cbuf if isinstance(Cbuf, C.c_void_p) else _ptr(Cbuf)
+        self.ctx.call("gcnb_spmm_csr_f32", C.byref(csr.struct), Bp, ldb, Cp, ldc, K, C.byref(epi))
+
+    def _gemm(self, tA, tB, M, N, K, A, lda, B, ldb, Cm, ldc, accumulate=0, bias=None, act=0):
+        def p(x):
+            return x if isinstance(x, C.c_void_p) or x is None else _ptr(x)
+        if M == 0:
+            return
+        self.ctx.call("gcnb_gemm_f32", tA, tB, M, N, K, p(A), lda, p(B), ldb, p(Cm), ldc, accumulate, p(bias), act)
+
+    def _gathered(self, x, ld):
+        """Dense operand of an A-SpMM: the local block itself, or its all-gather over ranks."""
+        if self.world == 1:
+            return x, x.shape[1]
+        out = self.gath.view(-1)[: self.n_tot * x.shape[1]].view(self.n_tot, x.shape[1])
+        torch.distributed.all_gather_into_tensor(out, x, group=self.group)
+        return out, x.shape[1]
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, train=False, seed=0, want_gates=False):
+        """Fill ``self.P`` (and the per-layer buffers) for the bound graph.  Asynchronous."""
+        L = self.layout
+        n = self.n_loc
+        hd = L.hid[0]
+        W0, ldw0 = self._pptr("W0")
+        b0, _ = self._pptr("b0")
+        p = self.drop_out if train else 0.0
+        # SparseInputDenseLayer + dropout: one SpMM with bias/act/dropout fused in the epilogue
+        self._spmm(self.X, W0, ldw0, self.H0, self.ldh[0], hd, bias=b0, act=self.act, dropout_p=p, seed=seed)
+        x, ldx, width = self.H0, self.ldh[0], hd
+        for i, l in enumerate(L.layers):
+            b = self.lay[i]
+            ldy = self.ldh[i + 1]
+            if l["kind"] == "hw":
+                k = l["i"]
+                Wh, ldwh = self._pptr("Wh%d" % k)
+                bh, _ = self._pptr("bh%d" % k)
+                Wt, ldwt = self._pptr("Wt%d" % k)
+                bt, _ = self._pptr("bt%d" % k)
+                xg, ldg = self._gathered(x, ldx)
+                S = self.S.view(-1)[: self.nbuf * ldx].view(self.nbuf, ldx)
+                self._spmm(self.A, xg, ldg, S, ldx, width)
+                self.ctx.call("gcnb_highway_fwd_f32", n, width, _ptr(S), ldx, _ptr(x), ldx, Wh, ldwh, bh, Wt, ldwt,
+                              bt, self.act, _ptr(b["Y"]), ldy, _ptr(b["H"]), ldy, _ptr(b["T"]), ldy)
+            else:
+                k = l["i"]
+                W, ldw = self._pptr("W%d" % k)
+                bb, _ = self._pptr("b%d" % k)
+                n_out = l["n_out"]
+                # reference order (gcnmodel.py:126-133): dense product first, then A, then bias
+                Q = self.S.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
+                self._gemm(0, 0, n, n_out, width, x, ldx, W, ldw, Q, ldy)
+                qg, ldg = self._gathered(Q, ldy)
+                self._spmm(self.A, qg, ldg, b["Y"], ldy, n_out, bias=bb, act=self.act)
+                width = n_out
+            x, ldx = b["Y"], ldy
+        self.x_last, self.ld_last, self.w_last = x, ldx, width
+        Wout, ldwo = self._pptr("Wout")
+        bout, _ = self._pptr("bout")
+        Cn = L.output_size
+        Q = self.S.view(-1)[: self.nbuf * self.ldc].view(self.nbuf, self.ldc)
+        self._gemm(0, 0, n, Cn, width, x, ldx, Wout, ldwo, Q, self.ldc)
+        qg, ldg = self._gathered(Q, self.ldc)
+        self._spmm(self.A_out, qg, ldg, self.P, self.ldc, Cn, bias=bout, softmax=1, logits=self.logits)
+        return self.P
+
+    # ------------------------------------------------------------------ backward + Adam
+    def backward(self, d_idx, d_lab, n_idx_local, n_train_global, seed):
+        L = self.layout
+        n = self.n_loc
+        Cn = L.output_size
+        csrT = self.A if self.AT is None else self.AT
+        self.ctx.call("gcnb_xent_grad_f32", _ptr(self.P), self.ldc, Cn, self.nbuf, _ptr(d_idx), _ptr(d_lab),
+                      n_idx_local, 1.0 / float(n_train_global), _ptr(self.G), self.ldc)
+        gg, ldg = self._gathered(self.G, self.ldc)
+        U = self.U.view(-1)[: self.nbuf * self.ldc].view(self.nbuf, self.ldc)
+        self._spmm(self.A_out if self.AT is None else self.AT_out, gg, ldg, U, self.ldc, Cn)
+        x, ldx, width = self.x_last, self.ld_last, self.w_last
+        gW, ldgw = self._gptr("Wout")
+        gb, _ = self._gptr("bout")
+        Wout, ldwo = self._pptr("Wout")
+        self._gemm(1, 0, width, Cn, n, x, ldx, U, self.ldc, gW, ldgw)          # dWout = x^T.U
+        self.ctx.call("gcnb_colsum_f32", n, Cn, _ptr(self.G), self.ldc, gb, 0)  # dbout
+        dX = self.dX.view(-1)[: self.nbuf * ldx].view(self.nbuf, ldx)
+        self._gemm(0, 1, n, width, Cn, U, self.ldc, Wout, ldwo, dX, ldx)        # dx = U.Wout^T
+        for i in reversed(range(len(L.layers))):
+            l = L.layers[i]
+            b = self.lay[i]
+            k = l["i"]
+            xin = self.lay[i - 1]["Y"] if i > 0 else self.H0
+            ldin = self.ldh[i]
+            n_in, n_out = l["n_in"], l["n_out"]
+            ldy = self.ldh[i + 1]
+            if l["kind"] == "hw":
+                dH = self.dH.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
+                dT = self.dT.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
+                # dHpre, dTpre, dx*(1-t) (in place over dX)
+                self.ctx.call("gcnb_highway_bwd_f32", n, n_out, ldy, _ptr(dX), _ptr(xin), _ptr(b["H"]), _ptr(b["T"]),
+                              self.act, _ptr(dH), _ptr(dT), _ptr(dX))
+                hg, ldg = self._gathered(dH, ldy)
+                V = self.U.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
+                self._spmm(csrT, hg, ldg, V, ldy, n_out)                            # V = A^T.dHpre
+                gWh, ldgh = self._gptr("Wh%d" % k)
+                gbh, _ = self._gptr("bh%d" % k)
+                gWt, ldgt = self._gptr("Wt%d" % k)
+                gbt, _ = self._gptr("bt%d" % k)
+                Wh, ldwh = self._pptr("Wh%d" % k)
+                Wt, ldwt = self._pptr("Wt%d" % k)
+                self._gemm(1, 0, n_in, n_out, n, xin, ldin, V, ldy, gWh, ldgh)      # dWh = x^T.V
+                self.ctx.call("gcnb_colsum_f32", n, n_out, _ptr(dH), ldy, gbh, 0)
+                self._gemm(0, 1, n, n_in, n_out, V, ldy, Wh, ldwh, dX, ldin, accumulate=1)   # dx += V.Wh^T
+                self._gemm(1, 0, n_in, n_out, n, xin, ldin, dT, ldy, gWt, ldgt)     # dWt = x^T.dTpre
+                self.ctx.call("gcnb_colsum_f32", n, n_out, _ptr(dT), ldy, gbt, 0)
+                self._gemm(0, 1, n, n_in, n_out, dT, ldy, Wt, ldwt, dX, ldin, accumulate=1)  # dx += dTpre.Wt^T
+            else:
+                dP = self.dH.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
+                self.ctx.call("gcnb_act_bwd_f32", n, n_out, ldy, _ptr(dX), _ptr(b["Y"]), self.act, 0.0, 0, 0, _ptr(dP))
+                pg, ldg = self._gathered(dP, ldy)
+                V = self.U.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
+                self._spmm(csrT, pg, ldg, V, ldy, n_out)
+                gW, ldgw = self._gptr("W%d" % k)
+                gb, _ = self._gptr("b%d" % k)
+                W, ldw = self._pptr("W%d" % k)
+                self._gemm(1, 0, n_in, n_out, n, xin, ldin, V, ldy, gW, ldgw)
+                self.ctx.call("gcnb_colsum_f32", n, n_out, _ptr(dP), ldy, gb, 0)
+                dXn = self.dX.view(-1)[: self.nbuf * ldin].view(self.nbuf, ldin)
+                self._gemm(0, 1, n, n_in, n_out, V, ldy, W, ldw, dXn, ldin)
+                dX = dXn
+        hd = L.hid[0]
+        ld0 = self.ldh[0]
+        dX = self.dX.view(-1)[: self.nbuf * ld0].view(self.nbuf, ld0)
+        p = self.drop_out
+        self.ctx.call("gcnb_act_bwd_f32", n, hd, ld0, _ptr(dX), _ptr(self.H0), self.act, p, int(seed) & (2**64 - 1),
+                      int(self.r0), _ptr(dX))
+        gW0, ldg0 = self._gptr("W0")
+        gb0, _ = self._gptr("b0")
+        self._spmm(self.XT, dX, ld0, gW0, ldg0, hd)                                 # dW0 = X^T.dz
+        self.ctx.call("gcnb_colsum_f32", n, hd, _ptr(dX), ld0, gb0, 0)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.grads, group=self.group)
+        if self.regul_coef > 0:
+            reg = C.c_void_p(self.metrics.data_ptr() + 4 * 4)
+            for off, size in L.weight_segments():
+                self.ctx.call("gcnb_l1l2_f32", C.c_void_p(self.params.data_ptr() + 4 * off),
+                              C.c_void_p(self.grads.data_ptr() + 4 * off), size, self.regul_coef, reg)
+
+    def adam_step(self, lr=2e-3, beta1=0.9, beta2=0.999, eps=1e-8):
+        self.ctx.call("gcnb_adam_f32", _ptr(self.params), _ptr(self.grads), _ptr(self.adam_m), _ptr(self.adam_v),
+                      self.layout.total, _ptr(self.adam_state), lr, beta1, beta2, eps)
+
+    def train_step(self, tr, dv, n_train, n_dev, seed, update=True):
+        """One ``f_train`` call (gcnmodel.py:409): metrics of the dropout output, then Adam.
+
+        ``tr`` / ``dv`` are ``index_arrays`` results.  Asynchronous; ``read_metrics`` syncs.
+        """
+        self.ctx.call("gcnb_memset", _ptr(self.metrics), 0, 32)
+        self.forward(train=True, seed=seed)
+        Cn = self.layout.output_size
+        self.ctx.call("gcnb_xent_metrics_f32", _ptr(self.P), self.ldc, Cn, _ptr(tr[0]), _ptr(tr[1]), tr[2],
+                      _ptr(self.metrics))
+        if dv is not None:
+            self.ctx.call("gcnb_xent_metrics_f32", _ptr(self.P), self.ldc, Cn, _ptr(dv[0]), _ptr(dv[1]), dv[2],
+                          C.c_void_p(self.metrics.data_ptr() + 8))
+        self.backward(tr[0], tr[1], tr[2], n_train, seed)
+        if update:
+            self.adam_step()
+        self.step_count += 1
+        self._n_train, self._n_dev = n_train, n_dev
+
+    def read_metrics(self):
+        """(train_loss, train_acc, dev_loss, dev_acc) of the last train_step; blocks."""
+        if self.world > 1:
+            torch.distributed.all_reduce(self.metrics[:4], group=self.group)
+        self.ctx.call("gcnb_d2h", C.c_void_p(self.metrics_host.data_ptr()), _ptr(self.metrics), 32)
+        self.ctx.sync()
+        m = self.metrics_host.numpy()
+        nt, nd = max(self._n_train, 1), max(self._n_dev, 1)
+        loss = float(m[0]) / nt + self.regul_coef * float(m[4])
+        return loss, float(m[1]) / nt, float(m[2]) / nd, float(m[3]) / nd
+
+    # ------------------------------------------------------------------ outputs
+    def gather_predictions(self, idx):
+        """argmax and probability rows of ``self.P`` at global indices ``idx`` (f_val outputs)."""
+        idx = np.ascontiguousarray(np.asarray(idx), dtype=np.int32)
+        Cn = self.layout.output_size
+        m = len(idx)
+        P = self.P
+        if self.world > 1:
+            full = torch.empty((self.n_tot, self.ldc), dtype=torch.float32, device=self.dev)
+            torch.distributed.all_gather_into_tensor(full, self.P, group=self.group)
+            P = full
+        self._keepalive = []
+        d_idx = self.upload(idx)
+        d_pred = torch.empty(max(m, 1), dtype=torch.int64, device=self.dev)
+        d_prob = torch.empty((max(m, 1), Cn), dtype=torch.float32, device=self.dev)
+        self.ctx.call("gcnb_gather_argmax_f32", _ptr(P), self.ldc, Cn, _ptr(d_idx), m, _ptr(d_pred), _ptr(d_prob))
+        preds = np.empty(m, dtype=np.int64)
+        probs = np.empty((m, Cn), dtype=np.float32)
+        if m:
+            self.ctx.call("gcnb_d2h", C.c_void_p(preds.ctypes.data), _ptr(d_pred), preds.nbytes)
+            self.ctx.call("gcnb_d2h", C.c_void_p(probs.ctypes.data), _ptr(d_prob), probs.nbytes)
+        self.ctx.sync()
+        self._keepalive = []
+        return preds, probs
+
+    def read_matrix(self, buf, rows, cols):
+        """Device (rows_pad x ld) buffer -> host ndarray (rows x cols), gathered over ranks."""
+        if self.world > 1:
+            full = torch.empty((self.n_tot, buf.shape[1]), dtype=torch.float32, device=self.dev)
+            torch.distributed.all_gather_into_tensor(full, buf.contiguous(), group=self.group)
+            buf = full
+        host = np.empty((buf.shape[0], buf.shape[1]), dtype=np.float32)
+        self.ctx.call("gcnb_d2h", C.c_void_p(host.ctypes.data), _ptr(buf), host.nbytes)
+        self.ctx.sync()
+        return np.ascontiguousarray(host[:rows, :cols])
+
+    def gates(self):
+        """Gate activations T_i of the last forward, one N x Hd array per highway layer."""
+        out = []
+        for l, b in zip(self.layout.layers, self.lay):
+            if l["kind"] == "hw":
+                out.append(self.read_matrix(b["T"], self.n, l["n_out"]))
+        return out
+
+    def dropout_mask(self, seed):
+        """Keep mask (N_local x Hd uint8) the fused epilogue draws for ``seed`` (tests feed the oracle)."""
+        hd = self.layout.hid[0]
+        m = torch.empty((max(self.n_loc, 1), hd), dtype=torch.uint8, device=self.dev)
+        self.ctx.call("gcnb_dropout_mask_u8", self.n_loc, hd, self.drop_out, int(seed) & (2**64 - 1), int(self.r0),
+                      _ptr(m))
+        host = np.empty((self.n_loc, hd), dtype=np.uint8)
+        if host.size:
+            self.ctx.call("gcnb_d2h", C.c_void_p(host.ctypes.data), _ptr(m), host.nbytes)
+        self.ctx.sync()
+        return host

@@ -74,34 +74,70 @@ def synthetic_graph(n, avg_degree, seed=77, alpha=None):
     return normalized_adjacency_from_edges(u, v, n)
 
 
-def synthetic_features(n, f, nnz_per_row, seed=77, zipf_s=1.1, chunk_rows=65536):
-    """N x F float32 CSR bag-of-words with Zipf term ids, binary-TF x IDF, L2-normalised rows."""
-    rng = np.random.RandomState(seed + 1)
+def _zipf_draws_for_unique(p, target):
+    """Number of with-replacement draws from pmf ``p`` whose expected count of distinct values is ``target``."""
+    lo, hi = float(target), float(target) * 64.0
+    l1p = np.log1p(-np.minimum(p, 1 - 1e-12))
+    for _ in range(60):
+        mid = 0.5 * (lo + hi)
+        if np.sum(-np.expm1(mid * l1p)) < target:
+            lo = mid
+        else:
+            hi = mid
+    return int(round(hi))
+
+
+def synthetic_features(n, f, nnz_per_row, seed=77, zipf_s=1.1, chunk_rows=32768, row_range=None):
+    """N x F float32 CSR bag-of-words: Zipf(1.1) term ids, binary TF x IDF, L2-normalised rows
+    (what data.py:275-278's TfidfVectorizer(binary=True, norm='l2') yields), about ``nnz_per_row``
+    distinct terms per row.
+
+    Rows are generated in independent chunks (own RNG stream per chunk) and the IDF comes from the
+    model's expected document frequency, so a rank can generate just its ``row_range`` = (r0, r1):
+    rows outside it are left empty in the returned N x F matrix.
+    """
     w = np.arange(1, f + 1, dtype=np.float64) ** (-zipf_s)
-    cdf = np.cumsum(w)
-    cdf /= cdf[-1]
-    term_of_rank = rng.permutation(f).astype(np.int64)  # frequent terms get arbitrary ids
-    col_chunks, cnt_chunks = [], []
-    for r0 in range(0, n, chunk_rows):
-        r1 = min(n, r0 + chunk_rows)
-        rr = r1 - r0
-        ranks = np.minimum(np.searchsorted(cdf, rng.random_sample(rr * nnz_per_row)), f - 1)
-        cols = term_of_rank[ranks]
-        keys = np.repeat(np.arange(rr, dtype=np.int64), nnz_per_row) * f + cols
-        keys = np.unique(keys)  # binary TF: a term counts once per row
+    p = w / w.sum()
+    cdf = np.cumsum(p)
+    cdf[-1] = 1.0
+    draws = _zipf_draws_for_unique(p, min(nnz_per_row, 0.5 * f))
+    term_of_rank = np.random.RandomState(seed + 1).permutation(f).astype(np.int64)  # frequent terms get arbitrary ids
+    df_rank = n * -np.expm1(draws * np.log1p(-np.minimum(p, 1 - 1e-12)))  # expected document frequency by rank
+    idf = np.empty(f, dtype=np.float64)
+    idf[term_of_rank] = np.log((1.0 + n) / (1.0 + df_rank)) + 1.0  # sklearn smooth_idf
+    chunk_rows = int(min(chunk_rows, max((2**31 - 1) // f, 1)))  # row*f + col fits int32
+    r_lo, r_hi = (0, n) if row_range is None else (int(row_range[0]), int(row_range[1]))
+    counts = np.zeros(n, dtype=np.int64)
+    col_chunks, val_chunks = [], []
+    for c0 in range(0, n, chunk_rows):
+        c1 = min(n, c0 + chunk_rows)
+        if c1 <= r_lo or c0 >= r_hi:
+            continue
+        rr = c1 - c0
+        rng = np.random.RandomState((seed * 1000003 + 7919 * (c0 // chunk_rows) + 11) % (2**32))
+        ranks = np.minimum(np.searchsorted(cdf, rng.random_sample(rr * draws)), f - 1)
+        keys = (np.repeat(np.arange(rr, dtype=np.int64), draws) * f + term_of_rank[ranks]).astype(np.int32)
+        keys.sort()
+        keys = keys[np.concatenate(([True], keys[1:] != keys[:-1]))]  # binary TF: a term counts once per row
         rows = keys // f
-        col_chunks.append((keys - rows * f).astype(np.int32))
-        cnt_chunks.append(np.bincount(rows, minlength=rr))
-    cols = np.concatenate(col_chunks)
-    counts = np.concatenate(cnt_chunks)
+        cols = keys - rows * f
+        cnt = np.bincount(rows, minlength=rr)
+        vals = idf[cols]
+        starts = np.concatenate(([0], np.cumsum(cnt)[:-1]))
+        sq = np.add.reduceat(vals * vals, np.minimum(starts, max(len(vals) - 1, 0))) if len(vals) else np.zeros(rr)
+        sq = np.where(cnt > 0, sq, 1.0)
+        vals = (vals / np.sqrt(np.repeat(sq, cnt))).astype(np.float32)
+        lo, hi = max(c0, r_lo) - c0, min(c1, r_hi) - c0  # keep only the requested rows of this chunk
+        if lo > 0 or hi < rr:
+            e0, e1 = starts[lo] if lo < rr else len(cols), (starts[hi] if hi < rr else len(cols))
+            cols, vals, cnt = cols[e0:e1], vals[e0:e1], cnt[lo:hi]
+        counts[c0 + lo:c0 + hi] = cnt
+        col_chunks.append(cols.astype(np.int32))
+        val_chunks.append(vals)
+    cols = np.concatenate(col_chunks) if col_chunks else np.zeros(0, np.int32)
+    vals = np.concatenate(val_chunks) if val_chunks else np.zeros(0, np.float32)
     rowptr = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(counts, out=rowptr[1:])
-    df = np.bincount(cols, minlength=f).astype(np.float64)
-    idf = np.log((1.0 + n) / (1.0 + df)) + 1.0  # sklearn smooth_idf
-    vals = idf[cols]
-    sq = np.add.reduceat(vals * vals, np.minimum(rowptr[:-1], max(len(vals) - 1, 0))) if len(vals) else np.zeros(n)
-    sq = np.where(counts > 0, sq, 1.0)
-    vals = (vals / np.sqrt(np.repeat(sq, counts))).astype(np.float32)
     X = sp.csr_matrix((vals, cols, rowptr.astype(np.int32)), shape=(n, f))
     X.has_sorted_indices = True
     return X
@@ -122,11 +158,13 @@ def split_indices(n):
     return idx[:n_tr], idx[n_tr:n_tr + n_dev], idx[n_tr + n_dev:]
 
 
-def synthetic_problem(name_or_cfg, seed=77, alpha=None):
-    """(A_hat, X, Y, train_idx, dev_idx, test_idx, cfg) for one of ``CONFIGS`` or a cfg dict."""
+def synthetic_problem(name_or_cfg, seed=77, alpha=None, row_range=None):
+    """(A_hat, X, Y, train_idx, dev_idx, test_idx, cfg) for one of ``CONFIGS`` or a cfg dict.
+    ``row_range`` = (r0, r1): generate only those rows of X (others empty) -- what one rank of a
+    row-partitioned run needs."""
     cfg = dict(CONFIGS[name_or_cfg]) if isinstance(name_or_cfg, str) else dict(name_or_cfg)
     A = synthetic_graph(cfg["n"], cfg["deg"], seed, alpha)
-    X = synthetic_features(cfg["n"], cfg["f"], cfg["xnnz"], seed)
+    X = synthetic_features(cfg["n"], cfg["f"], cfg["xnnz"], seed, row_range=row_range)
     Y = synthetic_labels(cfg["n"], cfg["classes"], seed)
     tr, dev, te = split_indices(cfg["n"])
     return A, X, Y, tr, dev, te, cfg

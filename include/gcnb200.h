@@ -54,7 +54,8 @@ enum gcnb_tag {
   GCNB_TAG_LOSS = 5,    /* softmax cross-entropy, argmax, gathers (gcnmodel.py:376-389) */
   GCNB_TAG_ADAM = 6,    /* lasagne.updates.adam (gcnmodel.py:407) */
   GCNB_TAG_COPY = 7,    /* host<->device copies issued through this ABI */
-  GCNB_NTAGS = 8
+  GCNB_TAG_SPMM_A_NARROW = 8, /* A_hat . (x Wout) and its gradient: K = classes, not the hidden width */
+  GCNB_NTAGS = 9
 };
 
 /* ---------------------------------------------------------------- context ------------- */

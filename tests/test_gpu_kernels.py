@@ -1,0 +1,170 @@
+"""Kernel-level parity on the GPU: every CUDA entry point of the C ABI against the oracle.
+
+Tolerance (BASELINE.json north_star): 1e-3 relative in fp32 for floating-point results, bit-exact
+for integer / index results (argmax, dropout mask)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import gcn_ref
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-3
+
+
+def _close(got, want, rtol=RTOL, atol_scale=1e-5):
+    want = np.asarray(want)
+    atol = atol_scale * max(float(np.abs(want).max()) if want.size else 0.0, 1e-30)
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=atol)
+
+
+def _rand_csr(rng, n, m, avg, hub_rows=(), hub_deg=0, empty_every=0):
+    deg = rng.poisson(avg, size=n)
+    if empty_every:
+        deg[::empty_every] = 0
+    deg[1::7] = 1
+    for r in hub_rows:
+        deg[r] = hub_deg
+    deg = np.minimum(deg, m)
+    rowptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(deg, out=rowptr[1:])
+    cols = np.concatenate([np.sort(rng.choice(m, size=d, replace=False)) for d in deg]) if rowptr[-1] else np.zeros(0)
+    vals = rng.randn(int(rowptr[-1])).astype(np.float32)
+    return sp.csr_matrix((vals, cols.astype(np.int32), rowptr.astype(np.int32)), shape=(n, m))
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("K", [1, 4, 129, 256, 300, 512, 600])
+def test_spmm_plain(K, variant):
+    from geographconv_b200 import layers
+    rng = np.random.RandomState(K)
+    A = _rand_csr(rng, 700, 900, 9, empty_every=5)
+    B = rng.randn(900, K).astype(np.float32)
+    got = layers.spmm(A, B, variant=variant)
+    _close(got, gcn_ref.structured_dot(A, B))
+    # rows without nonzeros are exactly zero
+    assert not got[np.diff(A.indptr) == 0].any()
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_spmm_hub_rows_split_deterministically(variant):
+    """A 100k-degree hub row (power-law graphs) is cut into items whose partial
+    sums are added in item order: same answer on every run."""
+    from geographconv_b200 import layers
+    rng = np.random.RandomState(7)
+    A = _rand_csr(rng, 300, 120_000, 6, hub_rows=(3, 250), hub_deg=100_000)
+    B = rng.randn(120_000, 300).astype(np.float32)
+    got = layers.spmm(A, B, variant=variant)
+    want = (A.astype(np.float64) @ B.astype(np.float64))
+    _close(got, want, atol_scale=2e-6)
+    again = layers.spmm(A, B, variant=variant)
+    np.testing.assert_array_equal(got, again)
+    other_chunk = layers.spmm(A, B, chunk=1024, variant=variant)
+    _close(other_chunk, want, atol_scale=2e-6)
+
+
+def test_spmm_empty_and_degenerate():
+    from geographconv_b200 import layers
+    rng = np.random.RandomState(0)
+    B = rng.randn(10, 8).astype(np.float32)
+    assert layers.spmm(sp.csr_matrix((0, 10), dtype=np.float32), B).shape == (0, 8)
+    Z = layers.spmm(sp.csr_matrix((5, 10), dtype=np.float32), B, bias=np.arange(8), act="linear")
+    np.testing.assert_array_equal(Z, np.tile(np.arange(8, dtype=np.float32), (5, 1)))
+    I = sp.identity(10, dtype=np.float32, format="csr")
+    np.testing.assert_array_equal(layers.spmm(I, B), B)
+
+
+@pytest.mark.parametrize("act", ["linear", "tanh", "relu", "sigmoid"])
+def test_spmm_bias_activation_epilogue(act):
+    from geographconv_b200 import layers
+    rng = np.random.RandomState(3)
+    A = _rand_csr(rng, 400, 500, 12)
+    B = (0.3 * rng.randn(500, 300)).astype(np.float32)
+    b = rng.randn(300).astype(np.float32)
+    got = layers.spmm(A, B, bias=b, act=act)
+    _close(got, gcn_ref._act(act)(gcn_ref.structured_dot(A, B) + b[None, :]), atol_scale=2e-5)
+
+
+def test_spmm_dropout_epilogue_matches_replayed_mask():
+    from geographconv_b200 import layers
+    rng = np.random.RandomState(4)
+    A = _rand_csr(rng, 300, 200, 10)
+    B = (0.3 * rng.randn(200, 300)).astype(np.float32)
+    b = rng.randn(300).astype(np.float32)
+    seed, row0, p = 0xDEADBEEF12345, 1000, 0.5
+    got = layers.spmm(A, B, bias=b, act="tanh", dropout_p=p, seed=seed, row0=row0)
+    keep = gcn_ref.dropout_keep_mask(seed, 300, 300, p, row0=row0)
+    want = np.tanh(gcn_ref.structured_dot(A, B) + b[None, :]) * keep / (1 - p)
+    _close(got, want, atol_scale=2e-5)
+    np.testing.assert_array_equal(got == 0, (keep == 0) | (want == 0))
+    assert abs(keep.mean() - 0.5) < 0.02
+
+
+@pytest.mark.parametrize("K", [7, 129, 256])
+def test_spmm_softmax_epilogue(K):
+    from geographconv_b200 import layers
+    rng = np.random.RandomState(K)
+    A = _rand_csr(rng, 350, 350, 8)
+    B = rng.randn(350, K).astype(np.float32)
+    b = rng.randn(K).astype(np.float32)
+    P, Z = layers.spmm(A, B, bias=b, softmax=True, want_logits=True)
+    zw = gcn_ref.structured_dot(A, B) + b[None, :]
+    _close(Z, zw)
+    _close(P, gcn_ref.softmax_rows(zw), atol_scale=1e-6)
+    np.testing.assert_allclose(P.sum(1), 1.0, rtol=1e-5)
+    clear = np.sort(zw, axis=1)
+    clear = (clear[:, -1] - clear[:, -2]) > 1e-4
+    np.testing.assert_array_equal(P.argmax(1)[clear], zw.argmax(1)[clear])
+
+
+def test_spmm_accumulate():
+    from geographconv_b200 import layers
+    rng = np.random.RandomState(5)
+    A = _rand_csr(rng, 200, 300, 10)
+    B = rng.randn(300, 300).astype(np.float32)
+    C0 = rng.randn(200, 300).astype(np.float32)
+    got = layers.spmm(A, B, accumulate_into=C0)
+    _close(got, C0 + gcn_ref.structured_dot(A, B))
+
+
+@pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(257, 300, 300), (1000, 129, 300), (300, 300, 5000), (3, 5, 2), (129, 300, 20000)])
+def test_gemm_simt(tA, tB, M, N, K):
+    from geographconv_b200 import layers
+    rng = np.random.RandomState(M + N + K)
+    A = rng.randn(K, M).astype(np.float32) if tA else rng.randn(M, K).astype(np.float32)
+    B = rng.randn(N, K).astype(np.float32) if tB else rng.randn(K, N).astype(np.float32)
+    want = (A.T if tA else A).astype(np.float64) @ (B.T if tB else B).astype(np.float64)
+    got = layers.gemm(A, B, transA=bool(tA), transB=bool(tB), tc=0)
+    _close(got, want, atol_scale=3e-6)
+
+
+def test_gemm_bias_act_and_accumulate():
+    from geographconv_b200 import layers
+    rng = np.random.RandomState(11)
+    A = (0.1 * rng.randn(500, 300)).astype(np.float32)
+    B = rng.randn(300, 300).astype(np.float32)
+    b = rng.randn(300).astype(np.float32)
+    _close(layers.gemm(A, B, bias=b, act="sigmoid", tc=0), gcn_ref.sigmoid(A @ B + b), atol_scale=1e-5)
+    C0 = rng.randn(500, 300).astype(np.float32)
+    _close(layers.gemm(A, B, accumulate_into=C0, tc=0), C0 + A @ B, atol_scale=1e-5)
+
+
+@pytest.mark.parametrize("tc", [0, 1])
+@pytest.mark.parametrize("n,hd", [(1000, 300), (777, 40), (129, 512)])
+def test_highway_forward(n, hd, tc):
+    from geographconv_b200 import layers
+    rng = np.random.RandomState(n)
+    S = rng.randn(n, hd).astype(np.float32)
+    X = rng.randn(n, hd).astype(np.float32)
+    Wh = (rng.randn(hd, hd) / np.sqrt(hd)).astype(np.float32)
+    Wt = (rng.randn(hd, hd) / np.sqrt(hd)).astype(np.float32)
+    bh = rng.randn(hd).astype(np.float32)
+    bt = (rng.randn(hd) - 1).astype(np.float32)
+    Y, H, T = layers.highway(S, X, Wh, bh, Wt, bt, tc=tc)
+    h = np.tanh(S.astype(np.float64) @ Wh + bh)
+    t = gcn_ref.sigmoid(X.astype(np.float64) @ Wt + bt)
+    _close(H, h, atol_scale=2e-5)
+    _close(T, t, atol_scale=2e-5)
+    _close(Y, t * h + (1 - t) * X, atol_scale=2e-5)

@@ -1,0 +1,119 @@
+"""Host logic: flat parameter layout, row blocks, and the row-partitioned exchange (world_size 2, gloo)."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from geographconv_b200 import partition, synth
+from oracle import gcn_ref
+
+
+def test_param_layout_roundtrip_highway_and_plain():
+    for highway, hid in [(True, [300, 300, 300]), (False, [40, 24, 56]), (True, [16])]:
+        L = partition.ParamLayout(100, hid, 129, highway)
+        params = gcn_ref.init_params(100, hid, 129, highway, 1)
+        flat = L.pack(params)
+        assert flat.size == L.total and L.total % 32 == 0
+        for e in L.entries:
+            assert e["offset"] % 32 == 0 and e["ld"] % 32 == 0
+        back = L.unpack(flat)
+        for a, b in zip(params, back):
+            np.testing.assert_array_equal(a, b)
+        # padding stays zero
+        assert flat.sum() == pytest.approx(sum(float(p.sum(dtype=np.float64)) for p in params), rel=1e-4, abs=1e-2)
+    L = partition.ParamLayout(100, [300, 300, 300], 129, True)
+    assert [e["name"] for e in L.entries] == ["W0", "b0", "Wt1", "bt1", "Wh1", "bh1", "Wt2", "bt2", "Wh2", "bh2",
+                                              "Wout", "bout"]
+    with pytest.raises(ValueError):
+        L.pack(gcn_ref.init_params(100, [300, 300], 129, True, 1))
+
+
+def test_row_blocks_and_index_split():
+    n_pad, blocks = partition.row_blocks(10, 4)
+    assert n_pad == 3 and blocks == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    n_pad, blocks = partition.row_blocks(5, 8)
+    assert n_pad == 1 and blocks[5] == (5, 5) and blocks[7] == (5, 5)
+    idx = np.array([9, 0, 4, 3, 5], dtype=np.int32)
+    lab = np.array([1, 2, 3, 4, 5], dtype=np.int32)
+    li, ll = partition.local_index_split(idx, lab, 3, 6)
+    assert li.tolist() == [1, 0, 2] and ll.tolist() == [3, 4, 5] and li.dtype == np.int32
+
+
+def test_symmetry_and_transpose():
+    A = synth.synthetic_graph(300, 6, 1)
+    assert partition.is_symmetric(A)
+    X = synth.synthetic_features(300, 50, 8, 1)
+    assert not partition.is_symmetric(X)
+    XT = partition.transpose_csr(X)
+    assert XT.shape == (50, 300) and XT.has_sorted_indices
+    np.testing.assert_allclose(XT.toarray(), X.toarray().T)
+
+
+def _rank_main(rank, world, port, q):
+    """Row-partitioned forward on CPU with the engine's exchange pattern (all-gather the dense
+    operand, local rows of A), gloo backend; compared with the single-process oracle."""
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        A, X, Y, tr, dev, te, cfg = synth.synthetic_problem(dict(n=101, deg=5, f=40, xnnz=6, hid=[12, 12, 12], classes=5))
+        params = gcn_ref.init_params(cfg["f"], cfg["hid"], cfg["classes"], True, 3)
+        n = cfg["n"]
+        n_pad, blocks = partition.row_blocks(n, world)
+        r0, r1 = blocks[rank]
+        n_tot = n_pad * world
+        Al = partition.slice_rows(A, r0, r1)
+        Al = sp.csr_matrix((Al.data, Al.indices, Al.indptr), shape=(r1 - r0, n_tot))
+        Xl = partition.slice_rows(X, r0, r1)
+
+        def gathered(x):
+            loc = np.zeros((n_pad, x.shape[1]), dtype=np.float32)
+            loc[: r1 - r0] = x
+            out = torch.empty((n_tot, x.shape[1]), dtype=torch.float32)
+            dist.all_gather_into_tensor(out, torch.from_numpy(loc))
+            return out.numpy()
+
+        W0, b0 = params[0], params[1]
+        x = np.tanh(Xl @ W0 + b0)
+        k = 2
+        for _ in range(2):
+            Wt, bt, Wh, bh = params[k:k + 4]
+            k += 4
+            h = np.tanh((Al @ gathered(x)) @ Wh + bh)
+            t = gcn_ref.sigmoid(x @ Wt + bt)
+            x = t * h + (1 - t) * x
+        logits = Al @ gathered(x @ params[k]) + params[k + 1]
+        probs = gcn_ref.softmax_rows(logits)
+        # loss pieces and weight-gradient all-reduce pattern: local partial sums, global mean
+        li, ll = partition.local_index_split(tr, Y[tr], r0, r1)
+        part = torch.tensor([float(-np.log(probs[li, ll]).sum()), float(len(li))], dtype=torch.float64)
+        dist.all_reduce(part)
+        full = gathered(probs)[:n]
+        q.put((rank, full, float(part[0] / part[1]), int(part[1])))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_partitioned_exchange_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    A, X, Y, tr, dev, te, cfg = synth.synthetic_problem(dict(n=101, deg=5, f=40, xnnz=6, hid=[12, 12, 12], classes=5))
+    params = gcn_ref.init_params(cfg["f"], cfg["hid"], cfg["classes"], True, 3)
+    ref = gcn_ref.forward(params, X, A, cfg["hid"], True)
+    want_loss = gcn_ref.cross_entropy(ref["probs"][tr], Y[tr])
+    for rank, full, loss, cnt in res:
+        np.testing.assert_allclose(full, ref["probs"], rtol=1e-4, atol=1e-6)
+        assert cnt == len(tr)
+        assert abs(loss - want_loss) < 1e-4
