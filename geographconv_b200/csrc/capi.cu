@@ -13,7 +13,7 @@ int gcnb_highway_tc(gcnb_ctx* ctx, int n_rows, int hd, const float* S, int lds, 
 bool gcnb_highway_tc_supported(const gcnb_ctx* ctx, int n_rows, int hd, int lds, int ldx, int ldwh, int ldwt);
 size_t gcnb_highway_tc_workspace_bytes(int hd);
 int gcnb_gemm_tc(gcnb_ctx* ctx, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
-                 float* C, int ldc, const float* bias, int act);
+                 float* C, int ldc, const float* bias, int act, int accumulate);
 bool gcnb_gemm_tc_supported(const gcnb_ctx* ctx, int transA, int transB, int M, int N, int K, int lda, int ldb,
                             int ldc, int accumulate);
 size_t gcnb_gemm_tc_workspace_bytes(int N, int K);
@@ -94,6 +94,7 @@ static int* option_slot(gcnb_ctx* ctx, const char* name) {
   if (!strcmp(name, "spmm_variant")) return &ctx->spmm_variant;
   if (!strcmp(name, "spmm_unroll")) return &ctx->spmm_unroll;
   if (!strcmp(name, "gemm_tc")) return &ctx->gemm_tc;
+  if (!strcmp(name, "tc_launches")) return &ctx->tc_launches;
   return nullptr;
 }
 extern "C" int gcnb_set_option(gcnb_ctx* ctx, const char* name, int value) {
@@ -192,7 +193,7 @@ extern "C" int gcnb_gemm_f32(gcnb_ctx* ctx, int32_t transA, int32_t transB, int3
   if (M == 0) return GCNB_OK;
   ProfScope scope(ctx, GCNB_TAG_GEMM);
   if (ctx->gemm_tc && gcnb_gemm_tc_supported(ctx, transA, transB, M, N, K, lda, ldb, ldc, accumulate))
-    return gcnb_gemm_tc(ctx, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, act);
+    return gcnb_gemm_tc(ctx, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, act, accumulate);
   return gcnb_gemm_simt(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, accumulate, bias, act);
 }
 

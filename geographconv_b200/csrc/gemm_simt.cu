@@ -157,10 +157,13 @@ int pick_splits(int M, int N, int K) {
 
 }  // namespace
 
+size_t gcnb_gemm_tc_workspace_bytes(int N, int K);
+
 extern "C" size_t gcnb_gemm_workspace_bytes(int32_t transA, int32_t M, int32_t N, int32_t K) {
-  (void)transA;
   const int s = pick_splits(M, N, K);
-  return s <= 1 ? 0 : (size_t)s * M * N * sizeof(float);
+  const size_t simt = s <= 1 ? 0 : (size_t)s * M * N * sizeof(float);
+  const size_t tc = transA ? 0 : gcnb_gemm_tc_workspace_bytes(N, K);  // transposed weight copy
+  return simt > tc ? simt : tc;
 }
 
 int gcnb_gemm_simt(gcnb_ctx* ctx, int transA, int transB, int M, int N, int K, const float* A, int lda,

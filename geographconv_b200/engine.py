@@ -182,7 +182,9 @@ class Engine:
             device = torch.cuda.current_device()
         self.dev = torch.device("cuda", int(device))
         torch.cuda.set_device(self.dev)
-        self.stream = torch.cuda.current_stream(self.dev)
+        # one dedicated (non-default) stream carries every kernel, copy and collective of the engine;
+        # torch allocations / fills happen on torch's current stream and are fenced by _fence()
+        self.stream = torch.cuda.Stream(self.dev)
         self.ctx = capi.Context(int(device), C.c_void_p(self.stream.cuda_stream))
         self.lib = self.ctx.lib
         L = layout
@@ -194,6 +196,7 @@ class Engine:
         # metrics: train {loss_sum, n_correct}, dev {loss_sum, n_correct}, reg_sum, pad
         self.metrics = torch.zeros(8, dtype=torch.float32, device=self.dev)
         self.metrics_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self._fence()
         self.ws = None
         self._keepalive = []
         self.n = None  # rows bound (global)
@@ -240,6 +243,10 @@ class Engine:
 
     def _zeros(self, rows, ld):
         return torch.zeros((max(rows, 1), ld), dtype=torch.float32, device=self.dev)
+
+    def _fence(self):
+        """Order torch-side fills (current stream) before engine-stream kernels that use the buffers."""
+        self.stream.wait_stream(torch.cuda.current_stream(self.dev))
 
     # ------------------------------------------------------------------ parameters
     def set_params(self, params):
@@ -332,6 +339,8 @@ class Engine:
         need = max(need, self.lib.gcnb_spmm_workspace_bytes(C.byref(self.A.struct), max(widths + [L.output_size])))
         need = max(need, self.lib.gcnb_spmm_workspace_bytes(C.byref(self.X.struct), hd))
         need = max(need, self.lib.gcnb_highway_workspace_bytes(0, max(widths)))
+        wall = max(widths + [L.output_size, hd])
+        need = max(need, self.lib.gcnb_gemm_workspace_bytes(0, max(n, 1), wall, wall))
         if need_backward:
             need = max(need, self.lib.gcnb_spmm_workspace_bytes(C.byref(self.XT.struct), hd))
             if self.AT is not None:
@@ -341,6 +350,7 @@ class Engine:
             need = max(need, self.lib.gcnb_gemm_workspace_bytes(1, wmax, wmax, max(n, 1)))
             need = max(need, self.lib.gcnb_colsum_workspace_bytes(n, wmax))
         self._ensure_ws(need)
+        self._fence()
 
     def index_arrays(self, idx, labels=None, force_upload=False):
         """Global node indices (+ their labels, aligned with ``idx``) -> device int32 arrays of this
@@ -397,7 +407,8 @@ class Engine:
         if self.world == 1:
             return x, x.shape[1]
         out = self.gath.view(-1)[: self.n_tot * x.shape[1]].view(self.n_tot, x.shape[1])
-        torch.distributed.all_gather_into_tensor(out, x, group=self.group)
+        with torch.cuda.stream(self.stream):
+            torch.distributed.all_gather_into_tensor(out, x, group=self.group)
         return out, x.shape[1]
 
     # ------------------------------------------------------------------ forward
@@ -521,7 +532,8 @@ class Engine:
         self._spmm(self.XT, dX, ld0, gW0, ldg0, hd)                                 # dW0 = X^T.dz
         self.ctx.call("gcnb_colsum_f32", n, hd, _ptr(dX), ld0, gb0, 0)
         if self.world > 1:
-            torch.distributed.all_reduce(self.grads, group=self.group)
+            with torch.cuda.stream(self.stream):
+                torch.distributed.all_reduce(self.grads, group=self.group)
         if self.regul_coef > 0:
             reg = C.c_void_p(self.metrics.data_ptr() + 4 * 4)
             for off, size in L.weight_segments():
@@ -554,7 +566,8 @@ class Engine:
     def read_metrics(self):
         """(train_loss, train_acc, dev_loss, dev_acc) of the last train_step; blocks."""
         if self.world > 1:
-            torch.distributed.all_reduce(self.metrics[:4], group=self.group)
+            with torch.cuda.stream(self.stream):
+                torch.distributed.all_reduce(self.metrics[:4], group=self.group)
         self.ctx.call("gcnb_d2h", C.c_void_p(self.metrics_host.data_ptr()), _ptr(self.metrics), 32)
         self.ctx.sync()
         m = self.metrics_host.numpy()
@@ -571,7 +584,8 @@ class Engine:
         P = self.P
         if self.world > 1:
             full = torch.empty((self.n_tot, self.ldc), dtype=torch.float32, device=self.dev)
-            torch.distributed.all_gather_into_tensor(full, self.P, group=self.group)
+            with torch.cuda.stream(self.stream):
+                torch.distributed.all_gather_into_tensor(full, self.P, group=self.group)
             P = full
         self._keepalive = []
         d_idx = self.upload(idx)
@@ -591,7 +605,8 @@ class Engine:
         """Device (rows_pad x ld) buffer -> host ndarray (rows x cols), gathered over ranks."""
         if self.world > 1:
             full = torch.empty((self.n_tot, buf.shape[1]), dtype=torch.float32, device=self.dev)
-            torch.distributed.all_gather_into_tensor(full, buf.contiguous(), group=self.group)
+            with torch.cuda.stream(self.stream):
+                torch.distributed.all_gather_into_tensor(full, buf.contiguous(), group=self.group)
             buf = full
         host = np.empty((buf.shape[0], buf.shape[1]), dtype=np.float32)
         self.ctx.call("gcnb_d2h", C.c_void_p(host.ctypes.data), _ptr(buf), host.nbytes)

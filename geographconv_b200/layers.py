@@ -28,9 +28,14 @@ class _Dev:
         device = torch.cuda.current_device() if device is None else int(device)
         self.dev = torch.device("cuda", device)
         torch.cuda.set_device(self.dev)
-        self.ctx = capi.Context(device, C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream))
+        self.stream = torch.cuda.Stream(self.dev)
+        self.ctx = capi.Context(device, C.c_void_p(self.stream.cuda_stream))
         self.ws = None
         self.spmm_chunk = 256
+
+    def fence(self):
+        """torch-side fills (current stream) happen-before the kernels on this context's stream."""
+        self.stream.wait_stream(torch.cuda.current_stream(self.dev))
 
     def ensure_ws(self, nbytes):
         nbytes = max(int(nbytes), 1 << 20)
@@ -120,6 +125,7 @@ def spmm(A, B, bias=None, act="linear", softmax=False, dropout_p=0.0, seed=0, ro
     epi.act, epi.softmax, epi.accumulate = ACT[act], int(bool(softmax)), int(accumulate_into is not None)
     epi.dropout_p, epi.seed, epi.row0 = float(dropout_p), int(seed), int(row0)
     epi.logits = dL.data_ptr() if dL is not None else None
+    d.fence()
     d.ctx.call("gcnb_spmm_csr_f32", C.byref(csr.struct), C.c_void_p(dB.data_ptr()), ldb, C.c_void_p(dC.data_ptr()), ldc,
                K, C.byref(epi))
     out = d.download(dC, rows, ldc, K)
@@ -148,12 +154,13 @@ def gemm(A, B, transA=False, transB=False, bias=None, act="linear", accumulate_i
         dC = torch.zeros(max(M, 1) * ldc, dtype=torch.float32, device=d.dev)
     db = d.vec(bias) if bias is not None else None
     d.ensure_ws(d.ctx.lib.gcnb_gemm_workspace_bytes(int(transA), M, N, K))
+    d.fence()
     d.ctx.call("gcnb_gemm_f32", int(transA), int(transB), M, N, K, C.c_void_p(dA.data_ptr()), lda,
                C.c_void_p(dB.data_ptr()), ldb, C.c_void_p(dC.data_ptr()), ldc, int(accumulate_into is not None),
                C.c_void_p(db.data_ptr()) if db is not None else None, ACT[act])
     out = d.download(dC, M, ldc, N)
     if tc is not None:
-        d.ctx.set_option("gemm_tc", 0)
+        d.ctx.set_option("gemm_tc", 1)
     return out
 
 
@@ -172,11 +179,12 @@ def highway(S, X, Wh, bh, Wt, bt, act="tanh", device=None, tc=None):
     outs = [torch.zeros(max(n, 1) * ld, dtype=torch.float32, device=d.dev) for _ in range(3)]
     d.ensure_ws(d.ctx.lib.gcnb_highway_workspace_bytes(n, hd))
     p = lambda t: C.c_void_p(t.data_ptr())
+    d.fence()
     d.ctx.call("gcnb_highway_fwd_f32", n, hd, p(dS), ld, p(dX), ld, p(dWh), ldw, p(dbh), p(dWt), ldw, p(dbt),
                ACT[act], p(outs[0]), ld, p(outs[1]), ld, p(outs[2]), ld)
     res = tuple(d.download(t, n, ld, hd) for t in outs)
     if tc is not None:
-        d.ctx.set_option("gemm_tc", 0)
+        d.ctx.set_option("gemm_tc", 1)
     return res
 
 

@@ -140,6 +140,35 @@ def test_gemm_simt(tA, tB, M, N, K):
     _close(got, want, atol_scale=3e-6)
 
 
+@pytest.mark.parametrize("tB", [0, 1])
+@pytest.mark.parametrize("M,N,K", [(257, 300, 300), (1000, 129, 300), (1000, 300, 256), (128, 32, 8), (3000, 512, 300),
+                                   (77, 5, 3), (130, 160, 1000)])
+def test_gemm_tcgen05_3xtf32(tB, M, N, K):
+    """tcgen05 path (3xTF32 split): fp32-grade accuracy against a float64 product."""
+    from geographconv_b200 import layers
+    rng = np.random.RandomState(M + N + K + tB)
+    A = rng.randn(M, K).astype(np.float32)
+    B = rng.randn(N, K).astype(np.float32) if tB else rng.randn(K, N).astype(np.float32)
+    want = A.astype(np.float64) @ (B.T if tB else B).astype(np.float64)
+    d = layers.get_dev()
+    before = d.ctx.get_option("tc_launches")
+    got = layers.gemm(A, B, transB=bool(tB), tc=1)
+    assert d.ctx.get_option("tc_launches") == before + 1, "the tcgen05 kernel did not run"
+    _close(got, want, atol_scale=3e-6)
+
+
+def test_gemm_tcgen05_bias_act_accumulate():
+    from geographconv_b200 import layers
+    rng = np.random.RandomState(12)
+    A = (0.1 * rng.randn(700, 300)).astype(np.float32)
+    B = rng.randn(300, 300).astype(np.float32)
+    b = rng.randn(300).astype(np.float32)
+    _close(layers.gemm(A, B, bias=b, act="tanh", tc=1), np.tanh(A.astype(np.float64) @ B + b), atol_scale=1e-5)
+    C0 = rng.randn(700, 300).astype(np.float32)
+    _close(layers.gemm(A, B, transB=True, accumulate_into=C0, tc=1), C0 + A.astype(np.float64) @ B.T.astype(np.float64),
+           atol_scale=1e-5)
+
+
 def test_gemm_bias_act_and_accumulate():
     from geographconv_b200 import layers
     rng = np.random.RandomState(11)
@@ -162,7 +191,10 @@ def test_highway_forward(n, hd, tc):
     Wt = (rng.randn(hd, hd) / np.sqrt(hd)).astype(np.float32)
     bh = rng.randn(hd).astype(np.float32)
     bt = (rng.randn(hd) - 1).astype(np.float32)
+    d = layers.get_dev()
+    before = d.ctx.get_option("tc_launches")
     Y, H, T = layers.highway(S, X, Wh, bh, Wt, bt, tc=tc)
+    assert d.ctx.get_option("tc_launches") == before + tc
     h = np.tanh(S.astype(np.float64) @ Wh + bh)
     t = gcn_ref.sigmoid(X.astype(np.float64) @ Wt + bt)
     _close(H, h, atol_scale=2e-5)
