@@ -17,6 +17,9 @@ int gcnb_gemm_tc(gcnb_ctx* ctx, int transB, int M, int N, int K, const float* A,
 bool gcnb_gemm_tc_supported(const gcnb_ctx* ctx, int transA, int transB, int M, int N, int K, int lda, int ldb,
                             int ldc, int accumulate);
 size_t gcnb_gemm_tc_workspace_bytes(int N, int K);
+int gcnb_wgrad_tc(gcnb_ctx* ctx, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+                  int ldc, int accumulate);
+bool gcnb_wgrad_tc_supported(const gcnb_ctx* ctx, int M, int N, int K, int lda, int ldb);
 
 extern "C" int gcnb_version(void) { return GCNB_VERSION; }
 
@@ -192,6 +195,9 @@ extern "C" int gcnb_gemm_f32(gcnb_ctx* ctx, int32_t transA, int32_t transB, int3
   GCNB_REQUIRE(ctx, lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N, "leading dimension too small");
   if (M == 0) return GCNB_OK;
   ProfScope scope(ctx, GCNB_TAG_GEMM);
+  if (ctx->gemm_tc && transA && !transB && !bias && act == GCNB_ACT_LINEAR &&
+      gcnb_wgrad_tc_supported(ctx, M, N, K, lda, ldb))
+    return gcnb_wgrad_tc(ctx, M, N, K, A, lda, B, ldb, C, ldc, accumulate);
   if (ctx->gemm_tc && gcnb_gemm_tc_supported(ctx, transA, transB, M, N, K, lda, ldb, ldc, accumulate))
     return gcnb_gemm_tc(ctx, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, act, accumulate);
   return gcnb_gemm_simt(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, accumulate, bias, act);

@@ -158,11 +158,14 @@ int pick_splits(int M, int N, int K) {
 }  // namespace
 
 size_t gcnb_gemm_tc_workspace_bytes(int N, int K);
+size_t gcnb_wgrad_tc_workspace_bytes(int M, int N, int K);
 
 extern "C" size_t gcnb_gemm_workspace_bytes(int32_t transA, int32_t M, int32_t N, int32_t K) {
   const int s = pick_splits(M, N, K);
   const size_t simt = s <= 1 ? 0 : (size_t)s * M * N * sizeof(float);
-  const size_t tc = transA ? 0 : gcnb_gemm_tc_workspace_bytes(N, K);  // transposed weight copy
+  // tcgen05 paths: transposed weight copy (activation x weight) or split-K partial tiles (wgrad)
+  const size_t tc = transA ? (M <= 1024 && N <= 1024 ? gcnb_wgrad_tc_workspace_bytes(M, N, K) : 0)
+                           : gcnb_gemm_tc_workspace_bytes(N, K);
   return simt > tc ? simt : tc;
 }
 

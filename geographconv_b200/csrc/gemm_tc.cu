@@ -334,6 +334,181 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// wgrad:  C[M x N] (+)= A^T . B with A: K x M and B: K x N row-major, K = number of graph nodes
+// (dW = x^T . V, gcnmodel.py:407's gradient of T.dot wrt W).  Both operands are "MN-major" for the
+// tensor core: a shared-memory tile holds 32-float column chunks, each [32 k-rows][128 B] with the
+// 128-byte swizzle TMA writes; the descriptor's LBO is the distance between chunks and one
+// tcgen05.mma consumes one 8-row k-group (1024 B).  The K range is split over CTAs (split-K); each
+// CTA stores its raw 128 x BN tile to a partial buffer that splitk_reduce adds in split order, so
+// the result does not depend on scheduling.
+// ---------------------------------------------------------------------------------------------
+struct alignas(64) WgParams {
+  CUtensorMap mapA;  // [K rows][M cols], box 32 x 32
+  CUtensorMap mapB;  // [K rows][N cols], box 32 x 32
+  int M, N, K, BN, m_tiles, n_tiles, splits, kb_per_split;
+  float* partial;    // [splits][M][N]
+};
+
+// MN-major descriptor for 32-bit operands: tf32 only accepts SWIZZLE_128B_BASE32B (layout type 1; 32-byte
+// units XOR-ed over a 4-row period, what TMA writes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
+// LBO = distance between 32-column chunks, SBO = distance between 4-row k-groups (512 B).
+__device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t saddr, uint32_t chunk_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(chunk_bytes >> 4) << 16) | (32ull << 32) | (1ull << 46) |
+         (1ull << 61);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int BN = p.BN;
+  constexpr uint32_t chunk_bytes = BK * 128;  // one 32-column chunk: 32 k-rows x 128 B
+  const uint32_t a_bytes = (BM / 32) * chunk_bytes, b_bytes = (uint32_t)(BN / 32) * chunk_bytes;
+  const uint32_t half_bytes = a_bytes + b_bytes;
+  const uint32_t stage_bytes = 2 * half_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * stage_bytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_full = smem_u32(bars), bar_conv = bar_full + 8 * kStages, bar_empty = bar_conv + 8 * kStages;
+  const uint32_t bar_acc = bar_empty + 8 * kStages;
+
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int tile = blockIdx.x % tiles, split = blockIdx.x / tiles;
+  const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
+  const int m0 = m_tile * BM, n0 = n_tile * BN;
+  const int kb0 = split * p.kb_per_split;
+  const int kb_total = (p.K + BK - 1) / BK;
+  int nkb = kb_total - kb0;
+  if (nkb > p.kb_per_split) nkb = p.kb_per_split;
+  if (nkb < 0) nkb = 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_conv + 8 * s, kConvWarps);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % kStages;
+        const uint32_t par = (it / kStages) & 1;
+        mbar_wait(bar_empty + 8 * s, par ^ 1);
+        mbar_expect_tx(bar_full + 8 * s, half_bytes);
+        const uint32_t dst = smem_base + s * stage_bytes;
+        const int k0 = (kb0 + it) * BK;
+        for (int c = 0; c < BM / 32; ++c) tma_load_2d(dst + c * chunk_bytes, &p.mapA, m0 + 32 * c, k0, bar_full + 8 * s);
+        for (int c = 0; c < BN / 32; ++c)
+          tma_load_2d(dst + a_bytes + c * chunk_bytes, &p.mapB, n0 + 32 * c, k0, bar_full + 8 * s);
+      }
+    }
+  } else if (warp == 1) {
+    // MN-major A and B: bits 15 and 16 of the instruction descriptor
+    const uint32_t idesc = umma_idesc_tf32(BN) | (1u << 15) | (1u << 16);
+    for (int it = 0; it < nkb; ++it) {
+      const int s = it % kStages;
+      const uint32_t par = (it / kStages) & 1;
+      mbar_wait(bar_conv + 8 * s, par);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t a_hi = smem_base + s * stage_bytes, b_hi = a_hi + a_bytes;
+        const uint32_t a_lo = a_hi + half_bytes, b_lo = b_hi + half_bytes;
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k)
+          umma_tf32(tmem_base, umma_desc_mn128(a_lo + 1024 * k, chunk_bytes), umma_desc_mn128(b_hi + 1024 * k, chunk_bytes), idesc, (it | k) != 0);
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k)
+          umma_tf32(tmem_base, umma_desc_mn128(a_hi + 1024 * k, chunk_bytes), umma_desc_mn128(b_lo + 1024 * k, chunk_bytes), idesc, 1u);
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k)
+          umma_tf32(tmem_base, umma_desc_mn128(a_hi + 1024 * k, chunk_bytes), umma_desc_mn128(b_hi + 1024 * k, chunk_bytes), idesc, 1u);
+        umma_commit(bar_empty + 8 * s);
+        if (it == nkb - 1) umma_commit(bar_acc);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int ct = threadIdx.x - 64;
+    const int n_chunks = (int)(half_bytes >> 4);
+    for (int it = 0; it < nkb; ++it) {
+      const int s = it % kStages;
+      const uint32_t par = (it / kStages) & 1;
+      mbar_wait(bar_full + 8 * s, par);
+      unsigned char* hi = smem + (size_t)s * stage_bytes;
+      unsigned char* lo = hi + half_bytes;
+      for (int c = ct; c < n_chunks; c += kConvWarps * 32) {
+        float4 v = *reinterpret_cast<const float4*>(hi + 16 * c);
+        float4 h, l;
+        uint32_t t;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t); l.x = v.x - h.x;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t); l.y = v.y - h.y;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t); l.z = v.z - h.z;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t); l.w = v.w - h.w;
+        *reinterpret_cast<float4*>(hi + 16 * c) = h;
+        *reinterpret_cast<float4*>(lo + 16 * c) = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_conv + 8 * s);
+    }
+    if (nkb > 0) {
+      mbar_wait(bar_acc, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int row = m0 + q * 32 + lane;
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* prow = p.partial + ((size_t)split * p.M + (size_t)row) * p.N;
+    for (int ch = half; ch < BN / 32; ch += 2) {
+      const int col0 = n0 + ch * 32;
+      if (col0 >= p.N) break;
+      float acc[32];
+      if (nkb > 0) tmem_ld32(tlane + (uint32_t)(ch * 32), acc);
+      else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+      }
+      if (row < p.M) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) prow[col0 + j] = acc[j];
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, float* C, int ldc,
+                                    int accumulate) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)M * N) return;
+  const int m = (int)(i / N), n = (int)(i % N);
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += partial[(long long)z * M * N + i];
+  float* dst = C + (long long)m * ldc + n;
+  *dst = accumulate ? *dst + s : s;
+}
+
 // Bt[n][k] = B[k][n]   (weights only: at most a few hundred rows/columns)
 __global__ void transpose_kernel(const float* __restrict__ B, int ldb, int K, int N, float* __restrict__ Bt, int ldbt) {
   __shared__ float tile[32][33];
@@ -366,7 +541,8 @@ EncodeTiledFn encode_fn() {
 }
 
 // 2-D fp32 tensor [rows][cols] (row stride ld floats), box = 32 columns x box_rows rows, 128B swizzle
-bool make_map(CUtensorMap* m, const float* base, long long rows, int cols, int ld, int box_rows) {
+bool make_map(CUtensorMap* m, const float* base, long long rows, int cols, int ld, int box_rows,
+              CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -374,7 +550,7 @@ bool make_map(CUtensorMap* m, const float* base, long long rows, int cols, int l
   cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -486,4 +662,64 @@ int gcnb_highway_tc(gcnb_ctx* ctx, int n_rows, int hd, const float* S, int lds, 
   p.C = Y; p.ldc = ldy; p.bias = bh; p.act = act; p.accumulate = 0;
   p.bias_t = bt; p.X = X; p.ldx = ldx; p.H = H; p.ldh = ldh; p.T = T; p.ldt = ldt;
   return launch(ctx, p);
+}
+
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct WgPlan { int BN, m_tiles, n_tiles, splits, kb_per_split; };
+WgPlan wgrad_plan(int sm_count, int M, int N, int K) {
+  WgPlan w;
+  pick_bn(N, &w.BN, &w.n_tiles);
+  w.m_tiles = (M + BM - 1) / BM;
+  const int tiles = w.m_tiles * w.n_tiles;
+  const int kb_total = (K + BK - 1) / BK;
+  int splits = sm_count / tiles;
+  if (splits < 1) splits = 1;
+  if (splits > kb_total) splits = kb_total > 0 ? kb_total : 1;
+  w.kb_per_split = (kb_total + splits - 1) / splits;
+  if (w.kb_per_split < 1) w.kb_per_split = 1;
+  w.splits = (kb_total + w.kb_per_split - 1) / w.kb_per_split;
+  if (w.splits < 1) w.splits = 1;
+  return w;
+}
+}  // namespace
+
+bool gcnb_wgrad_tc_supported(const gcnb_ctx* ctx, int M, int N, int K, int lda, int ldb) {
+  (void)ctx;
+  if (M < 1 || N < 1 || K < 1) return false;
+  if (M > 1024 || N > 1024) return false;  // weight-shaped outputs only
+  if ((lda % 4) != 0 || (ldb % 4) != 0) return false;
+  return encode_fn() != nullptr;
+}
+
+size_t gcnb_wgrad_tc_workspace_bytes(int M, int N, int K) {
+  const WgPlan w = wgrad_plan(148, M, N, K);
+  return (size_t)(w.splits + 1) * M * N * sizeof(float);
+}
+
+int gcnb_wgrad_tc(gcnb_ctx* ctx, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+                  int ldc, int accumulate) {
+  GCNB_REQUIRE(ctx, aligned16(A) && aligned16(B), "tcgen05 wgrad: 16-byte aligned matrices");
+  const WgPlan w = wgrad_plan(ctx->sm_count, M, N, K);
+  const size_t need = (size_t)w.splits * M * N * sizeof(float);
+  if (!ctx->ws || ctx->ws_bytes < need)
+    return gcnb_fail(ctx, GCNB_E_WORKSPACE, "tcgen05 wgrad needs %s%lld workspace bytes, have %lld", "",
+                     (long long)need, (long long)ctx->ws_bytes);
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  if (!make_map(&p.mapA, A, K, M, lda, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+      !make_map(&p.mapB, B, K, N, ldb, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+    return gcnb_fail(ctx, GCNB_E_CUDA, "cuTensorMapEncodeTiled failed%s", "");
+  p.M = M; p.N = N; p.K = K; p.BN = w.BN; p.m_tiles = w.m_tiles; p.n_tiles = w.n_tiles;
+  p.splits = w.splits; p.kb_per_split = w.kb_per_split;
+  p.partial = reinterpret_cast<float*>(ctx->ws);
+  const size_t smem = smem_bytes(p.BN);
+  GCNB_CUDA(ctx, cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  wgrad_tc_kernel<<<(unsigned)(w.m_tiles * w.n_tiles * w.splits), kThreads, smem, ctx->stream>>>(p);
+  GCNB_LAUNCHED(ctx);
+  ctx->tc_launches++;
+  const long long n = (long long)M * N;
+  wgrad_reduce_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(p.partial, w.splits, M, N, C, ldc, accumulate);
+  GCNB_LAUNCHED(ctx);
+  return GCNB_OK;
 }

@@ -157,6 +157,25 @@ def test_gemm_tcgen05_3xtf32(tB, M, N, K):
     _close(got, want, atol_scale=3e-6)
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 300, 5000), (129, 300, 20000), (300, 256, 777), (40, 24, 100), (512, 512, 4096),
+                                   (300, 300, 31), (7, 3, 5)])
+def test_wgrad_tcgen05_split_k(M, N, K):
+    """dW = x^T . V on tensor cores: MN-major operands, split over the node dimension, deterministic."""
+    from geographconv_b200 import layers
+    rng = np.random.RandomState(M + N + K)
+    A = rng.randn(K, M).astype(np.float32)
+    B = rng.randn(K, N).astype(np.float32)
+    want = A.T.astype(np.float64) @ B.astype(np.float64)
+    d = layers.get_dev()
+    before = d.ctx.get_option("tc_launches")
+    got = layers.gemm(A, B, transA=True, tc=1)
+    assert d.ctx.get_option("tc_launches") == before + 1, "the tcgen05 wgrad kernel did not run"
+    _close(got, want, atol_scale=3e-6)
+    np.testing.assert_array_equal(got, layers.gemm(A, B, transA=True, tc=1))
+    C0 = rng.randn(M, N).astype(np.float32)
+    _close(layers.gemm(A, B, transA=True, accumulate_into=C0, tc=1), C0 + want, atol_scale=3e-6)
+
+
 def test_gemm_tcgen05_bias_act_accumulate():
     from geographconv_b200 import layers
     rng = np.random.RandomState(12)
