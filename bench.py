@@ -272,7 +272,8 @@ def run_gpu(args, cfg, wname):
             dist.all_reduce(tms2, op=dist.ReduceOp.MIN)  # slowest rank's kernel
         ach = float(tms2.item())
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic, "kernel": "spmm_ldg_kernel (A_hat.H, K=%d)" % hd,
+                "traffic": traffic,
+                "kernel": "%s (A_hat.H, K=%d)" % ("spmm_bulk_kernel" if (hd > 256 and N / world * 1280 > (96 << 20)) else "spmm_ldg_kernel", hd),
                 "algorithmic_bytes_per_launch": b_touch, "launches_timed": spmm_ops,
                 "avg_launch_ms": spmm_ms / spmm_ops, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
                 "per_rank": world > 1}

@@ -28,7 +28,7 @@ class GcnbCsr(C.Structure):
         ("rowptr", C.c_void_p), ("colidx", C.c_void_p), ("val", C.c_void_p),
         ("items", C.c_void_p), ("n_items", C.c_int32),
         ("long_rows", C.c_void_p), ("n_long", C.c_int32), ("n_slots", C.c_int32),
-        ("tag", C.c_int32),
+        ("tag", C.c_int32), ("engine", C.c_int32), ("unroll", C.c_int32),
     ]
 
 

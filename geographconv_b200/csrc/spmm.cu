@@ -373,10 +373,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_fixup_kernel(const Spm
 }
 
 template <int NCHUNK>
-int launch_pass(gcnb_ctx* ctx, const SpmmParams& p) {
+int launch_pass(gcnb_ctx* ctx, const SpmmParams& p, int engine, int unroll) {
   const int grid = cdiv(p.n_items, kWarpsPerCta);
   if (p.n_items > 0) {
-    if (ctx->spmm_variant == 1) {
+    if (engine == 1) {
       constexpr int STAGES = NCHUNK == 4 ? 3 : 4, WARPS = 8;
       const uint32_t row_bytes = (uint32_t)p.nf4 * 16u;
       const uint32_t slot_bytes = (row_bytes + 127u) & ~127u;
@@ -392,8 +392,8 @@ int launch_pass(gcnb_ctx* ctx, const SpmmParams& p) {
       kern<<<g, WARPS * 32, smem, ctx->stream>>>(p);
       GCNB_LAUNCHED(ctx);
     } else {
-      int U = ctx->spmm_unroll;
-      if (U == 0) U = NCHUNK <= 2 ? 8 : 4;
+      int U = unroll;
+      if (U == 0) U = NCHUNK <= 2 ? 8 : 2;
       if (U >= 8) spmm_ldg_kernel<NCHUNK, 8><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(p);
       else if (U >= 4) spmm_ldg_kernel<NCHUNK, 4><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(p);
       else spmm_ldg_kernel<NCHUNK, 2><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(p);
@@ -477,7 +477,17 @@ extern "C" int gcnb_spmm_csr_f32(gcnb_ctx* ctx, const gcnb_csr* A, const float* 
   }
   if (A->n_rows == 0) return GCNB_OK;
   const size_t need = gcnb_spmm_workspace_bytes(A, K);
-  if (A->n_slots > 0 || ctx->spmm_variant == 1) {
+  int engine = A->engine >= 0 ? A->engine : ctx->spmm_variant;
+  int unroll = A->unroll > 0 ? A->unroll : ctx->spmm_unroll;
+  if (A->engine == -2) {
+    // auto (measured on B200, profiles/r1_spmm_sweep.txt): when the gathered operand cannot live in L2 and a row
+    // spans more than 64 float4 lanes (K > 256) the bulk-copy staged engine reaches 91% of the HBM copy rate vs
+    // 71-78% for register gathers; L2-resident operands and narrower rows are fastest with LDG, 2 nonzeros/batch
+    const size_t operand_bytes = (size_t)A->n_cols * (size_t)ldb * sizeof(float);
+    engine = (operand_bytes > ((size_t)96 << 20) && K4 > 256) ? 1 : 0;
+    if (unroll == 0) unroll = 2;
+  }
+  if (A->n_slots > 0 || engine == 1) {
     if (!ctx->ws || ctx->ws_bytes < need)
       return gcnb_fail(ctx, GCNB_E_WORKSPACE, "spmm needs %s%lld workspace bytes, have %lld", "", (long long)need,
                        (long long)ctx->ws_bytes);
@@ -511,10 +521,10 @@ extern "C" int gcnb_spmm_csr_f32(gcnb_ctx* ctx, const gcnb_csr* A, const float* 
     const int nchunk = (p.nf4 + 31) / 32;
     int rc;
     switch (nchunk) {
-      case 1: rc = launch_pass<1>(ctx, p); break;
-      case 2: rc = launch_pass<2>(ctx, p); break;
-      case 3: rc = launch_pass<3>(ctx, p); break;
-      default: rc = launch_pass<4>(ctx, p); break;
+      case 1: rc = launch_pass<1>(ctx, p, engine, unroll); break;
+      case 2: rc = launch_pass<2>(ctx, p, engine, unroll); break;
+      case 3: rc = launch_pass<3>(ctx, p, engine, unroll); break;
+      default: rc = launch_pass<4>(ctx, p, engine, unroll); break;
     }
     if (rc != GCNB_OK) return rc;
   }

@@ -37,7 +37,7 @@ from . import capi
 from .capi import ACT, GcnbCsr, GcnbEpilogue
 from .partition import ParamLayout, ld_of, local_index_split, row_blocks, slice_rows, transpose_csr, is_symmetric
 
-SPMM_CHUNK_DEFAULT = 256  # nonzeros per row item (rows longer than this are split; see gcnb_csr_plan)
+SPMM_CHUNK_DEFAULT = 1024  # nonzeros per row item (rows longer than this are split; see gcnb_csr_plan)
 
 
 def _ptr(t):
@@ -136,6 +136,7 @@ class DeviceCsr:
         s.items, s.n_items = self.t_items.data_ptr(), host.n_items
         s.long_rows = self.t_long.data_ptr() if host.n_long else None
         s.n_long, s.n_slots, s.tag = host.n_long, host.n_slots, int(tag)
+        s.engine, s.unroll = -2, 0  # gather engine chosen per call from operand size and K (spmm.cu)
         self.struct = s
         self.refill(eng, host)
 

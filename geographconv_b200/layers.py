@@ -96,6 +96,7 @@ class CsrOnDevice:
         s.n_items = len(items)
         s.long_rows = self.keep[4].data_ptr() if len(long_rows) else None
         s.n_long, s.n_slots, s.tag = len(long_rows), int(n_slots), int(tag)
+        s.engine, s.unroll = -1, 0  # the context options decide (tests sweep them)
         self.struct = s
         self.shape = M.shape
 

@@ -105,6 +105,12 @@ typedef struct gcnb_csr {
   int32_t n_long;
   int32_t n_slots;
   int32_t tag; /* gcnb_tag the SpMM time is booked under */
+  /* gather engine for this matrix: 0 = LDG.128 register gather (best when the dense operand is L2
+   * resident, e.g. X.W0), 1 = bulk-copy (TMA engine) staged gather with persistent CTAs (best when
+   * the gathered rows come from HBM, e.g. A_hat.H), -1 = the context's "spmm_variant" option,
+   * -2 = choose per call from the operand size and K */
+  int32_t engine;
+  int32_t unroll; /* nonzeros gathered per batch by engine 0 (2, 4, 8); 0 = the context's / auto */
 } gcnb_csr;
 
 /* Host-side planning over a HOST rowptr.  Call once with items == NULL to get the counts, then

@@ -1,0 +1,94 @@
+#!/usr/bin/env python
+"""SpMM micro-benchmark on the GPU box: A_hat.H / X.W0 / X^T.dz at BASELINE shapes, gather-engine variants.
+
+    python tools/spmm_sweep.py [--n 500000] [--deg 32] [--k 300] [--alpha 2.0] [--what a,x,xt]
+Prints one line per configuration: ms per launch, B_touch GB/s, fraction of the measured HBM peak.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from geographconv_b200 import capi, synth  # noqa: E402
+from geographconv_b200.engine import DeviceCsr, HostCsr  # noqa: E402
+from geographconv_b200.partition import ld_of, transpose_csr  # noqa: E402
+
+
+class Mini:
+    def __init__(self):
+        self.dev = torch.device("cuda", 0)
+        self.stream = torch.cuda.Stream(self.dev)
+        self.ctx = capi.Context(0, C.c_void_p(self.stream.cuda_stream))
+        self.ws = torch.empty(1 << 30, dtype=torch.uint8, device=self.dev)
+        self.ctx.call("gcnb_set_workspace", C.c_void_p(self.ws.data_ptr()), self.ws.numel())
+
+
+def time_spmm(m, csr, B, ldb, Cbuf, ldc, K, reps=5):
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    for i in range(2 + reps):
+        if i == 2:
+            ev[0].record(m.stream)
+        m.ctx.call("gcnb_spmm_csr_f32", C.byref(csr.struct), C.c_void_p(B.data_ptr()), ldb, C.c_void_p(Cbuf.data_ptr()),
+                   ldc, K, None)
+    ev[1].record(m.stream)
+    torch.cuda.synchronize()
+    return ev[0].elapsed_time(ev[1]) / reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=500000)
+    ap.add_argument("--deg", type=int, default=32)
+    ap.add_argument("--k", type=int, default=300)
+    ap.add_argument("--f", type=int, default=50000)
+    ap.add_argument("--xnnz", type=int, default=256)
+    ap.add_argument("--alpha", type=float, default=None)
+    ap.add_argument("--what", default="a")
+    ap.add_argument("--chunks", default="256")
+    ap.add_argument("--variants", default="0:0,0:2,0:4,0:8,1:0")
+    args = ap.parse_args()
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    m = Mini()
+    K, ld = args.k, ld_of(args.k)
+    mats = {}
+    if "a" in args.what.split(","):
+        mats["A_hat.H"] = (synth.synthetic_graph(args.n, args.deg, 77, args.alpha), args.n)
+    if "x" in args.what.split(",") or "xt" in args.what.split(","):
+        X = synth.synthetic_features(args.n, args.f, args.xnnz, 77)
+        if "x" in args.what.split(","):
+            mats["X.W0"] = (X, args.f)
+        if "xt" in args.what.split(","):
+            mats["X^T.dz"] = (transpose_csr(X), args.n)
+    for name, (M, brows) in mats.items():
+        B = torch.randn(brows, ld, device=m.dev)
+        B[:, K:] = 0
+        Cbuf = torch.zeros(M.shape[0], ld, device=m.dev)
+        m.stream.wait_stream(torch.cuda.current_stream())
+        deg = np.diff(M.indptr)
+        print("%s: rows %d nnz %d max-row %d  K=%d" % (name, M.shape[0], M.nnz, int(deg.max()), K), flush=True)
+        for chunk in [int(c) for c in args.chunks.split(",")]:
+            class E:  # what DeviceCsr needs from an engine
+                dev, ctx = m.dev, m.ctx
+            csr = DeviceCsr(E, HostCsr(M, chunk), 0)
+            csr.struct.engine, csr.struct.unroll = -1, 0
+            m.ctx.sync()
+            for v in args.variants.split(","):
+                var, unroll = [int(x) for x in v.split(":")]
+                m.ctx.set_option("spmm_variant", var)
+                m.ctx.set_option("spmm_unroll", unroll)
+                ms = time_spmm(m, csr, B, ld, Cbuf, ld, K)
+                gbs = csr.touched_bytes(K) / ms / 1e6
+                print("  chunk %5d variant %d unroll %d: %8.3f ms  %7.1f GB/s  %.3f of HBM peak  (items %d, long rows %d)"
+                      % (chunk, var, unroll, ms, gbs, gbs / peak, csr.n_items, csr.n_long), flush=True)
+
+
+if __name__ == "__main__":
+    main()
