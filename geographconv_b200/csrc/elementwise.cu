@@ -252,6 +252,19 @@ __global__ void dropout_mask_kernel(int n_rows, int k, uint32_t thresh, uint64_t
   }
 }
 
+// dst[i] = src[idx[i]] (gather) or dst[idx[i]] = src[i] (scatter), float4 rows
+__global__ void move_rows_kernel(const float* src, int ld_src, const int* idx, int n_idx, int nf4, float* dst,
+                                 int ld_dst, int scatter) {
+  const long long total = (long long)n_idx * nf4;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(t / nf4), c = (int)(t % nf4);
+    const int r = idx[i];
+    const size_t rs = scatter ? (size_t)i : (size_t)r, rd = scatter ? (size_t)r : (size_t)i;
+    st4(dst, rd, ld_dst, c, ld4(src, rs, ld_src, c));
+  }
+}
+
 inline int grid_for(const gcnb_ctx* ctx, long long work_items) {
   long long g = (work_items + kThreads - 1) / kThreads;
   const long long cap = (long long)ctx->sm_count * 16;
@@ -418,4 +431,27 @@ extern "C" int gcnb_dropout_mask_u8(gcnb_ctx* ctx, int32_t n_rows, int32_t k, fl
   dropout_mask_kernel<<<grid_for(ctx, total), kThreads, 0, ctx->stream>>>(n_rows, k, thresh_of(p), seed, row0, mask);
   GCNB_LAUNCHED(ctx);
   return GCNB_OK;
+}
+
+static int move_rows(gcnb_ctx* ctx, const float* src, int ld_src, const int* idx, int n_idx, int k, float* dst,
+                     int ld_dst, int scatter) {
+  if (!ctx) return GCNB_E_INVALID;
+  GCNB_REQUIRE(ctx, src && dst && (n_idx == 0 || idx), "null pointer");
+  const int k4 = ((k + 3) / 4) * 4;
+  GCNB_REQUIRE(ctx, ld_src % 4 == 0 && ld_dst % 4 == 0 && ld_src >= k4 && ld_dst >= k4, "ld: multiple of 4, >= k rounded to 4");
+  if (n_idx == 0 || k == 0) return GCNB_OK;
+  ProfScope scope(ctx, GCNB_TAG_ELEM);
+  const int nf4 = k4 / 4;
+  move_rows_kernel<<<grid_for(ctx, (long long)n_idx * nf4), kThreads, 0, ctx->stream>>>(src, ld_src, idx, n_idx, nf4,
+                                                                                        dst, ld_dst, scatter);
+  GCNB_LAUNCHED(ctx);
+  return GCNB_OK;
+}
+extern "C" int gcnb_gather_rows_f32(gcnb_ctx* ctx, const float* src, int32_t ld_src, const int32_t* idx, int32_t n_idx,
+                                    int32_t k, float* dst, int32_t ld_dst) {
+  return move_rows(ctx, src, ld_src, idx, n_idx, k, dst, ld_dst, 0);
+}
+extern "C" int gcnb_scatter_rows_f32(gcnb_ctx* ctx, const float* src, int32_t ld_src, const int32_t* idx,
+                                     int32_t n_idx, int32_t k, float* dst, int32_t ld_dst) {
+  return move_rows(ctx, src, ld_src, idx, n_idx, k, dst, ld_dst, 1);
 }

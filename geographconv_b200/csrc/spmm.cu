@@ -65,6 +65,17 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, floa
   for (int ch = 0; ch < NCHUNK; ++ch) {
     v[ch][0] = acc[ch].x; v[ch][1] = acc[ch].y; v[ch][2] = acc[ch].z; v[ch][3] = acc[ch].w;
   }
+  if (p.accumulate == 2) {  // pre-activation accumulate: the product joins what C already holds (dense hot-column part)
+    const float4* crow_in = reinterpret_cast<const float4*>(p.C + (size_t)row * p.ldc + p.col0);
+#pragma unroll
+    for (int ch = 0; ch < NCHUNK; ++ch) {
+      const int f4 = lane + 32 * ch;
+      if (f4 < p.nf4) {
+        const float4 c = crow_in[f4];
+        v[ch][0] += c.x; v[ch][1] += c.y; v[ch][2] += c.z; v[ch][3] += c.w;
+      }
+    }
+  }
   if (p.bias != nullptr) {
 #pragma unroll
     for (int ch = 0; ch < NCHUNK; ++ch) {
@@ -143,7 +154,7 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, floa
     const int f4 = lane + 32 * ch;
     if (f4 < p.nf4) {
       float4 o = make_float4(v[ch][0], v[ch][1], v[ch][2], v[ch][3]);
-      if (p.accumulate) {
+      if (p.accumulate == 1) {
         const float4 old = crow[f4];
         o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
       }

@@ -124,7 +124,8 @@ typedef struct gcnb_epilogue {
   const float* bias;   /* device, K floats padded to a multiple of 4 with zeros; or NULL */
   int32_t act;         /* gcnb_act */
   int32_t softmax;     /* 1: row softmax over the K columns after the bias (K <= 512) */
-  int32_t accumulate;  /* 1: C += out */
+  int32_t accumulate;  /* 0: C = out.  1: C += out.  2: C = epilogue(C + A.B): the product is added to what C
+                        * already holds BEFORE bias / activation / dropout / softmax */
   float dropout_p;     /* 0: none.  Inverted dropout, scale 1/(1-p) (lasagne DropoutLayer) */
   uint64_t seed;       /* Philox key */
   int64_t row0;        /* global index of local row 0 (row-partitioned runs draw the same mask) */
@@ -174,6 +175,13 @@ int gcnb_act_bwd_f32(gcnb_ctx* ctx, int32_t n_rows, int32_t k, int32_t ld, const
 int gcnb_colsum_f32(gcnb_ctx* ctx, int32_t n_rows, int32_t k, const float* A, int32_t lda,
                     float* out, int32_t accumulate);
 size_t gcnb_colsum_workspace_bytes(int32_t n_rows, int32_t k);
+
+/* dst[i, :k] = src[idx[i], :k] for i < n_idx (rows of a weight matrix selected by column id: the dense
+ * hot-column block of X multiplies W0[hot, :]).  scatter: dst[idx[i], :k] = src[i, :k]. */
+int gcnb_gather_rows_f32(gcnb_ctx* ctx, const float* src, int32_t ld_src, const int32_t* idx, int32_t n_idx,
+                         int32_t k, float* dst, int32_t ld_dst);
+int gcnb_scatter_rows_f32(gcnb_ctx* ctx, const float* src, int32_t ld_src, const int32_t* idx, int32_t n_idx,
+                          int32_t k, float* dst, int32_t ld_dst);
 
 /* ---------------------------------------------------------------- loss / outputs ------ */
 /* metrics[0] += sum_i -log P[idx[i], labels[i]];  metrics[1] += #(argmax P[idx[i]] == labels[i])
