@@ -115,6 +115,13 @@ extern "C" int gcnb_get_option(const gcnb_ctx* ctx, const char* name, int* value
   return GCNB_OK;
 }
 
+// debug hook (not part of the public header): per-CTA clock64 phase stamps of the fused highway kernel
+extern "C" int gcnb_debug_set_tc_buffer(gcnb_ctx* ctx, void* dev_ptr) {
+  if (!ctx) return GCNB_E_INVALID;
+  ctx->tc_dbg = dev_ptr;
+  return GCNB_OK;
+}
+
 extern "C" int gcnb_sync(gcnb_ctx* ctx) {
   if (!ctx) return GCNB_E_INVALID;
   GCNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -7,14 +7,15 @@
 //
 // Precision: the reference computes in fp32 (BLAS sgemm).  kind::tf32 alone (10-bit mantissa) misses
 // the 1e-3 parity budget after a few layers, so every product is done as an error-compensated
-// 3xTF32 split: a = a_hi + a_lo with a_hi = rn_tf32(a), a_lo = a - a_hi (exact in fp32);
+// 3xTF32 split: a = a_hi + a_lo with a_hi = a truncated to tf32, a_lo = a - a_hi (exact in fp32);
 // A.B ~= A_lo.B_hi + A_hi.B_lo + A_hi.B_hi, all accumulated in fp32 in TMEM (error ~2^-21).
 //
 // Structure (one 128 x BN output tile per CTA, 320 threads, 1 CTA / SM):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes (128B-swizzled) of raw fp32 A and Bt
 //               tiles into a 3-stage shared-memory ring, completion on `full` mbarriers;
-//   warps 2-9   converters: split every landed tile in place into hi (tf32-rounded) and a second
-//               `lo` tile with the same swizzled layout, fence.proxy.async, arrive on `conv`;
+//   warps 2-9   converters: for every landed tile write the residual `lo` = a - tf32_trunc(a) into a second
+//               tile with the same swizzled layout (the raw tile is the hi operand), fence.proxy.async,
+//               arrive on `conv`;
 //   warp 1      allocates TMEM, one elected lane issues 12 tcgen05.mma.kind::tf32 (M128 x BN x K8)
 //               per 32-wide k-block, tcgen05.commit releases the stage (`empty`) and finally
 //               signals `acc_full`;
@@ -36,7 +37,10 @@ constexpr int kMaxBN = 160;
 
 struct alignas(64) TcParams {
   CUtensorMap mapA[2];
-  CUtensorMap mapB[2];
+  CUtensorMap mapB[2];    // weights, hi part (raw fp32; the tensor core drops the low 13 mantissa bits)
+  CUtensorMap mapBlo[2];  // weights, residual lo part, pre-split by split_weights_kernel
+  CUtensorMap mapIn;      // X tile (highway) or C tile (accumulate): boxes of 32 columns x 128 rows
+  CUtensorMap mapOut[3];  // plain: C; highway: Y, H, T
   int nphase;      // 1: plain GEMM, 2: fused highway (phase 0 = S.Wh, phase 1 = X.Wt)
   int kblocks[2];  // 32-wide k-blocks per phase
   int M, N, BN, n_tiles;
@@ -53,6 +57,7 @@ struct alignas(64) TcParams {
   int ldh;
   float* T;
   int ldt;
+  long long* dbg;  // optional per-CTA phase timestamps (tools/gemm_phases.py)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -84,6 +89,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
       "l"(map), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1)
+               : "memory");
 }
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 8-row groups
 // 1024 B apart (SBO), LBO = 1 (unused for swizzled K-major), version 1, layout type 2.
@@ -123,22 +133,34 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ float sigmoidf_(float z) { return 1.f / (1.f + expf(-z)); }
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Epilogue activations: ex2.approx / rcp.approx based (abs error ~1e-7, far inside the 1e-3 parity budget); the
+// accurate libm forms are ~60 instructions per element and made the 8-warp epilogue latency bound.
+__device__ __forceinline__ float sigmoidf_(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
+__device__ __forceinline__ float tanhf_(float z) {
+  const float e = __expf(2.f * z);          // inf for large z -> 1, 0 for very negative z -> -1
+  return 1.f - __fdividef(2.f, e + 1.f);
+}
 
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024-byte alignment of every tile (SWIZZLE_128B atoms are 8 rows x 128 B)
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const long long t_enter = clock64();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int BN = p.BN;
   const uint32_t a_bytes = BM * 128, b_bytes = (uint32_t)BN * 128;
   const uint32_t half_bytes = a_bytes + b_bytes;   // [A_hi | B_hi] then [A_lo | B_lo]
   const uint32_t stage_bytes = 2 * half_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * stage_bytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 2);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_full = smem_u32(bars), bar_conv = bar_full + 8 * kStages, bar_empty = bar_conv + 8 * kStages;
-  const uint32_t bar_acc = bar_empty + 8 * kStages;
+  const uint32_t bar_acc = bar_empty + 8 * kStages, bar_in = bar_acc + 8;
 
   const int n_tile = blockIdx.x % p.n_tiles, m_tile = blockIdx.x / p.n_tiles;
   const int m0 = m_tile * BM, n0 = n_tile * BN;
@@ -150,6 +172,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_acc, 1);
+    mbar_init(bar_in, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -163,20 +186,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const int total_kb = p.kblocks[0] + (p.nphase > 1 ? p.kblocks[1] : 0);
+  long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 16 : nullptr;
+  if (dbg && threadIdx.x == 64) { dbg[0] = t_enter; dbg[1] = clock64(); unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); dbg[6] = sm; dbg[7] = globaltimer_ns(); }
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int it = 0;
+      long long w_empty = 0;
       for (int ph = 0; ph < p.nphase; ++ph) {
         for (int kb = 0; kb < p.kblocks[ph]; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t par = (it / kStages) & 1;
+          const long long t0 = dbg ? clock64() : 0;
           mbar_wait(bar_empty + 8 * s, par ^ 1);
-          mbar_expect_tx(bar_full + 8 * s, half_bytes);
+          if (dbg) { w_empty += clock64() - t0; dbg[8] = w_empty; }
+          mbar_expect_tx(bar_full + 8 * s, a_bytes + 2 * b_bytes);
           const uint32_t dst = smem_base + s * stage_bytes;
           tma_load_2d(dst, &p.mapA[ph], kb * BK, m0, bar_full + 8 * s);
           tma_load_2d(dst + a_bytes, &p.mapB[ph], kb * BK, n0, bar_full + 8 * s);
+          tma_load_2d(dst + half_bytes + a_bytes, &p.mapBlo[ph], kb * BK, n0, bar_full + 8 * s);
         }
       }
     }
@@ -184,12 +213,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc = umma_idesc_tf32(BN);
     int it = 0;
+    long long w_conv = 0;
     for (int ph = 0; ph < p.nphase; ++ph) {
       const uint32_t tacc = tmem_base + (uint32_t)(ph * BN);
       for (int kb = 0; kb < p.kblocks[ph]; ++kb, ++it) {
         const int s = it % kStages;
         const uint32_t par = (it / kStages) & 1;
+        const long long t0 = dbg ? clock64() : 0;
         mbar_wait(bar_conv + 8 * s, par);
+        if (dbg && lane == 0) { w_conv += clock64() - t0; dbg[9] = w_conv; }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (lane == 0) {
           const uint32_t a_hi = smem_base + s * stage_bytes, b_hi = a_hi + a_bytes;
@@ -213,119 +245,173 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   } else {
     // ------------------------------------------------------------------ converters, then epilogue
     const int ct = threadIdx.x - 64;  // 0 .. 255
-    const int n_chunks = (int)(half_bytes >> 4);
+    long long w_full = 0, t_cv = 0;
     for (int it = 0; it < total_kb; ++it) {
       const int s = it % kStages;
       const uint32_t par = (it / kStages) & 1;
+      const long long t0 = dbg ? clock64() : 0;
       mbar_wait(bar_full + 8 * s, par);
-      unsigned char* hi = smem + (size_t)s * stage_bytes;
-      unsigned char* lo = hi + half_bytes;
-      for (int c = ct; c < n_chunks; c += kConvWarps * 32) {
-        float4 v = *reinterpret_cast<const float4*>(hi + 16 * c);
-        float4 h, l;
-        uint32_t t;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t); l.x = v.x - h.x;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t); l.y = v.y - h.y;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t); l.z = v.z - h.z;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t); l.w = v.w - h.w;
-        *reinterpret_cast<float4*>(hi + 16 * c) = h;
-        *reinterpret_cast<float4*>(lo + 16 * c) = l;
+      const long long t1 = dbg ? clock64() : 0;
+      if (dbg && ct == 0) { w_full += t1 - t0; dbg[10] = w_full; }
+      if (dbg && ct == 0 && it == 0) dbg[2] = clock64();
+      // Only the activation tile needs splitting here (the weights arrive pre-split): 128 rows x 128 B = 1024
+      // 16-byte chunks, 4 per thread.  The tensor core reads tf32 operands from the fp32 words as they are and
+      // ignores the low 13 mantissa bits, so the raw tile IS the hi operand; only lo = a - hi is written.
+      const unsigned char* hi = smem + (size_t)s * stage_bytes;
+      unsigned char* lo = smem + (size_t)s * stage_bytes + half_bytes;
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(hi + 16 * (ct + 256 * u));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float4 l;
+        l.x = v[u].x - __uint_as_float(__float_as_uint(v[u].x) & 0xffffe000u);
+        l.y = v[u].y - __uint_as_float(__float_as_uint(v[u].y) & 0xffffe000u);
+        l.z = v[u].z - __uint_as_float(__float_as_uint(v[u].z) & 0xffffe000u);
+        l.w = v[u].w - __uint_as_float(__float_as_uint(v[u].w) & 0xffffe000u);
+        *reinterpret_cast<float4*>(lo + 16 * (ct + 256 * u)) = l;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor core reads
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_conv + 8 * s);
+      if (dbg && ct == 0) { t_cv += clock64() - t1; dbg[11] = t_cv; }
     }
 
+    if (dbg && ct == 0) dbg[3] = clock64();
     mbar_wait(bar_acc, 0);
+    if (dbg && ct == 0) dbg[4] = clock64();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ---- epilogue: TMEM -> registers -> swizzled shared-memory boxes -> TMA stores (coalesced, clipped at M / N).
+    // The pipeline stages are free now; they are re-used as [IN boxes | OUT staging of group 0 | group 1].
+    // Warps 2-5 form group 0, warps 6-9 group 1; a group owns every second 32-column chunk of the tile.
+    constexpr uint32_t kBox = BM * 128;  // one box: 128 rows x 32 columns fp32, SWIZZLE_128B
+    const int nch = BN / 32;
     const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;  // two warps share a quarter: interleave the 32-column chunks
-    const int row = m0 + q * 32 + lane;
+    const int grp = (warp - 2) >> 2;
+    const int r = q * 32 + lane;       // row of the tile this thread owns
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-    const bool row_ok = row < p.M;
-    for (int ch = half; ch < BN / 32; ch += 2) {
+    const bool need_in = (p.nphase == 2) || p.accumulate;
+    const int n_out = p.nphase == 2 ? 3 : 1;
+    unsigned char* in_base = smem;
+    unsigned char* out_base = smem + (need_in ? (size_t)nch * kBox : 0) + (size_t)grp * n_out * kBox;
+    if (need_in) {
+      if (ct == 0) {
+        mbar_expect_tx(bar_in, (uint32_t)nch * kBox);
+        for (int c = 0; c < nch; ++c) tma_load_2d(smem_base + c * kBox, &p.mapIn, n0 + 32 * c, m0, bar_in);
+      }
+      mbar_wait(bar_in, 0);
+    }
+    long long e_ld = 0, e_math = 0, e_out = 0;
+    if (dbg && ct == 0) dbg[12] = clock64() - dbg[4];
+    const uint32_t swz = (uint32_t)(r & 7);
+    const uint32_t bar_id = 1 + grp;
+    const bool leader = (ct & 127) == 0;
+    bool first = true;
+    for (int ch = grp; ch < nch; ch += 2) {
       const int col0 = n0 + ch * 32;
-      if (col0 >= p.N) break;  // warp-uniform
+      if (col0 >= p.N) break;  // uniform over the group
       float acc[32];
+      const long long s0 = dbg ? clock64() : 0;
       tmem_ld32(tlane + (uint32_t)(ch * 32), acc);
-      if (p.nphase == 1) {
-        float* crow = p.C + (size_t)row * p.ldc + col0;
+      const long long s1 = dbg ? clock64() : 0;
+      float xin[32];
+      if (need_in) {
+        const unsigned char* ib = in_base + (size_t)ch * kBox + (size_t)r * 128;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float o[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int col = col0 + j + e;
-            float v = acc[j + e];
-            if (!p.accumulate) {
-              if (p.bias != nullptr && col < p.N) v += __ldg(p.bias + col);
-              v = act_apply(p.act, v);
-            }
-            o[e] = v;
-          }
-          if (row_ok) {
-            if (col0 + j + 3 < p.N) {
-              float4 w = make_float4(o[0], o[1], o[2], o[3]);
-              if (p.accumulate) {
-                const float4 old = *reinterpret_cast<const float4*>(crow + j);
-                w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
-              }
-              *reinterpret_cast<float4*>(crow + j) = w;
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (col0 + j + e < p.N) crow[j + e] = p.accumulate ? crow[j + e] + o[e] : o[e];
-            }
-          }
+        for (int j = 0; j < 8; ++j) {
+          const float4 v = *reinterpret_cast<const float4*>(ib + ((j ^ swz) << 4));
+          xin[4 * j] = v.x; xin[4 * j + 1] = v.y; xin[4 * j + 2] = v.z; xin[4 * j + 3] = v.w;
         }
+      }
+      if (!first) {  // the previous chunk's TMA stores must have read the staging boxes
+        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      }
+      first = false;
+      unsigned char* ob = out_base + (size_t)r * 128;
+      const bool full_chunk = col0 + 32 <= p.N;  // bias vectors are only guaranteed up to N rounded to 4
+      if (p.nphase == 1) {
+        const bool use_bias = !p.accumulate && p.bias != nullptr;
+        auto body = [&](auto act_fn) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float b[4] = {0.f, 0.f, 0.f, 0.f};
+            if (use_bias) {
+              if (full_chunk) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+                b[0] = bv.x; b[1] = bv.y; b[2] = bv.z; b[3] = bv.w;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (col0 + 4 * j + e < p.N) b[e] = __ldg(p.bias + col0 + 4 * j + e);
+              }
+            }
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              o[e] = p.accumulate ? acc[4 * j + e] + xin[4 * j + e] : act_fn(acc[4 * j + e] + b[e]);
+            *reinterpret_cast<float4*>(ob + ((j ^ swz) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        };
+        if (p.accumulate || p.act == GCNB_ACT_LINEAR) body([](float z) { return z; });
+        else if (p.act == GCNB_ACT_TANH) body([](float z) { return tanhf_(z); });
+        else if (p.act == GCNB_ACT_SIGMOID) body([](float z) { return sigmoidf_(z); });
+        else body([](float z) { return fmaxf(z, 0.f); });
       } else {
         float acc_t[32];
         tmem_ld32(tlane + (uint32_t)(BN + ch * 32), acc_t);
-        const float* xrow = p.X + (size_t)row * p.ldx + col0;
-        float* yrow = p.C + (size_t)row * p.ldc + col0;
-        float* hrow = p.H ? p.H + (size_t)row * p.ldh + col0 : nullptr;
-        float* trow = p.T ? p.T + (size_t)row * p.ldt + col0 : nullptr;
+        auto body = [&](auto act_fn) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float h[4], t[4], y[4], x[4] = {0.f, 0.f, 0.f, 0.f};
-          const bool full4 = col0 + j + 3 < p.N;
-          if (row_ok) {
-            if (full4) {
-              const float4 xv = *reinterpret_cast<const float4*>(xrow + j);
-              x[0] = xv.x; x[1] = xv.y; x[2] = xv.z; x[3] = xv.w;
+          for (int j = 0; j < 8; ++j) {
+            float bh[4] = {0.f, 0.f, 0.f, 0.f}, bt[4] = {0.f, 0.f, 0.f, 0.f};
+            if (full_chunk) {
+              const float4 u = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+              const float4 w = __ldg(reinterpret_cast<const float4*>(p.bias_t + col0) + j);
+              bh[0] = u.x; bh[1] = u.y; bh[2] = u.z; bh[3] = u.w;
+              bt[0] = w.x; bt[1] = w.y; bt[2] = w.z; bt[3] = w.w;
             } else {
 #pragma unroll
               for (int e = 0; e < 4; ++e)
-                if (col0 + j + e < p.N) x[e] = xrow[j + e];
-            }
-          }
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int col = col0 + j + e;
-            const bool ok = col < p.N;
-            h[e] = act_apply(p.act, acc[j + e] + (ok ? __ldg(p.bias + col) : 0.f));
-            t[e] = sigmoidf_(acc_t[j + e] + (ok ? __ldg(p.bias_t + col) : 0.f));
-            y[e] = t[e] * h[e] + (1.0f - t[e]) * x[e];
-          }
-          if (row_ok) {
-            if (full4) {
-              *reinterpret_cast<float4*>(yrow + j) = make_float4(y[0], y[1], y[2], y[3]);
-              if (hrow) *reinterpret_cast<float4*>(hrow + j) = make_float4(h[0], h[1], h[2], h[3]);
-              if (trow) *reinterpret_cast<float4*>(trow + j) = make_float4(t[0], t[1], t[2], t[3]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (col0 + j + e < p.N) {
-                  yrow[j + e] = y[e];
-                  if (hrow) hrow[j + e] = h[e];
-                  if (trow) trow[j + e] = t[e];
+                if (col0 + 4 * j + e < p.N) {
+                  bh[e] = __ldg(p.bias + col0 + 4 * j + e);
+                  bt[e] = __ldg(p.bias_t + col0 + 4 * j + e);
                 }
             }
+            float h[4], t[4], y[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              h[e] = act_fn(acc[4 * j + e] + bh[e]);
+              t[e] = sigmoidf_(acc_t[4 * j + e] + bt[e]);
+              y[e] = t[e] * h[e] + (1.0f - t[e]) * xin[4 * j + e];
+            }
+            const uint32_t off = (j ^ swz) << 4;
+            *reinterpret_cast<float4*>(ob + off) = make_float4(y[0], y[1], y[2], y[3]);
+            *reinterpret_cast<float4*>(ob + kBox + off) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(ob + 2 * kBox + off) = make_float4(t[0], t[1], t[2], t[3]);
           }
+        };
+        if (p.act == GCNB_ACT_TANH) body([](float z) { return tanhf_(z); });
+        else if (p.act == GCNB_ACT_SIGMOID) body([](float z) { return sigmoidf_(z); });
+        else if (p.act == GCNB_ACT_RELU) body([](float z) { return fmaxf(z, 0.f); });
+        else body([](float z) { return z; });
+      }
+      const long long s2 = dbg ? clock64() : 0;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      if (dbg && ct == 0) { e_ld += s1 - s0; e_math += s2 - s1; e_out += clock64() - s2; dbg[13] = e_ld; dbg[14] = e_math; dbg[15] = e_out; }
+      if (leader) {
+        const uint32_t src = smem_u32(out_base);
+        tma_store_2d(&p.mapOut[0], src, col0, m0);
+        if (p.nphase == 2) {
+          if (p.H) tma_store_2d(&p.mapOut[1], src + kBox, col0, m0);
+          if (p.T) tma_store_2d(&p.mapOut[2], src + 2 * kBox, col0, m0);
         }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (dbg && ct == 0) dbg[5] = clock64();
   }
   __syncthreads();
   if (warp == 1) {
@@ -452,14 +538,14 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
       unsigned char* hi = smem + (size_t)s * stage_bytes;
       unsigned char* lo = hi + half_bytes;
       for (int c = ct; c < n_chunks; c += kConvWarps * 32) {
-        float4 v = *reinterpret_cast<const float4*>(hi + 16 * c);
-        float4 h, l;
-        uint32_t t;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t); l.x = v.x - h.x;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t); l.y = v.y - h.y;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t); l.z = v.z - h.z;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t); l.w = v.w - h.w;
-        *reinterpret_cast<float4*>(hi + 16 * c) = h;
+        // The tensor core reads tf32 operands from the fp32 words as they are and ignores the low 13 mantissa
+        // bits, so the raw tile IS the hi operand (hi = a with those bits dropped); only lo = a - hi is written.
+        const float4 v = *reinterpret_cast<const float4*>(hi + 16 * c);
+        float4 l;
+        l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+        l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+        l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+        l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
         *reinterpret_cast<float4*>(lo + 16 * c) = l;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -509,18 +595,32 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int split
   *dst = accumulate ? *dst + s : s;
 }
 
-// Bt[n][k] = B[k][n]   (weights only: at most a few hundred rows/columns)
-__global__ void transpose_kernel(const float* __restrict__ B, int ldb, int K, int N, float* __restrict__ Bt, int ldbt) {
+// Weight operand prep (weights only: at most a few hundred rows / columns): Bt[n][k] = op(B) as an N x K
+// row-major matrix (transposing when B is stored K x N) and its 3xTF32 residual Blo = Bt - tf32_trunc(Bt).
+__global__ void split_weights_kernel(const float* __restrict__ B, int ldb, int K, int N, int transpose,
+                                     float* __restrict__ Bt, float* __restrict__ Blo, int ldbt) {
   __shared__ float tile[32][33];
   const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int k = k0 + i, n = n0 + threadIdx.x;
-    tile[i][threadIdx.x] = (k < K && n < N) ? B[(size_t)k * ldb + n] : 0.f;
+    float v = 0.f;
+    if (transpose) {  // B is K x N
+      const int k = k0 + i, n = n0 + threadIdx.x;
+      if (k < K && n < N) v = B[(size_t)k * ldb + n];
+      tile[i][threadIdx.x] = v;
+    } else {          // B is N x K already
+      const int n = n0 + i, k = k0 + threadIdx.x;
+      if (k < K && n < N) v = B[(size_t)n * ldb + k];
+      tile[threadIdx.x][i] = v;
+    }
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int n = n0 + i, k = k0 + threadIdx.x;
-    if (n < N && k < K) Bt[(size_t)n * ldbt + k] = tile[threadIdx.x][i];
+    if (n < N && k < K) {
+      const float v = tile[threadIdx.x][i];
+      Bt[(size_t)n * ldbt + k] = v;
+      Blo[(size_t)n * ldbt + k] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    }
   }
 }
 
@@ -561,7 +661,7 @@ void pick_bn(int N, int* bn, int* n_tiles) {
   *n_tiles = (N + *bn - 1) / *bn;
 }
 
-size_t smem_bytes(int BN) { return (size_t)kStages * 2 * (BM * 128 + BN * 128) + (3 * kStages + 1) * 8 + 16 + 1024; }
+size_t smem_bytes(int BN) { return (size_t)kStages * 2 * (BM * 128 + BN * 128) + (3 * kStages + 2) * 8 + 16 + 1024; }
 
 int launch(gcnb_ctx* ctx, const TcParams& p) {
   const size_t smem = smem_bytes(p.BN);
@@ -573,9 +673,9 @@ int launch(gcnb_ctx* ctx, const TcParams& p) {
   return GCNB_OK;
 }
 
-int transpose_into_ws(gcnb_ctx* ctx, const float* B, int ldb, int K, int N, float* Bt, int ldbt) {
+int split_weights(gcnb_ctx* ctx, const float* B, int ldb, int K, int N, int transpose, float* Bt, float* Blo, int ldbt) {
   dim3 grid(cdiv(N, 32), cdiv(K, 32)), block(32, 8);
-  transpose_kernel<<<grid, block, 0, ctx->stream>>>(B, ldb, K, N, Bt, ldbt);
+  split_weights_kernel<<<grid, block, 0, ctx->stream>>>(B, ldb, K, N, transpose, Bt, Blo, ldbt);
   GCNB_LAUNCHED(ctx);
   return GCNB_OK;
 }
@@ -594,7 +694,7 @@ bool gcnb_gemm_tc_supported(const gcnb_ctx* ctx, int transA, int transB, int M, 
   return encode_fn() != nullptr;
 }
 
-size_t gcnb_gemm_tc_workspace_bytes(int N, int K) { return (size_t)N * ld32(K) * sizeof(float); }
+size_t gcnb_gemm_tc_workspace_bytes(int N, int K) { return 2 * (size_t)N * ld32(K) * sizeof(float); }
 
 int gcnb_gemm_tc(gcnb_ctx* ctx, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                  float* C, int ldc, const float* bias, int act, int accumulate) {
@@ -603,20 +703,20 @@ int gcnb_gemm_tc(gcnb_ctx* ctx, int transB, int M, int N, int K, const float* A,
   TcParams p;
   memset(&p, 0, sizeof(p));
   pick_bn(N, &p.BN, &p.n_tiles);
-  const float* Bt = B;
-  int ldbt = ldb;
-  if (!transB) {  // B is K x N: the kernel wants N x K
-    const size_t need = gcnb_gemm_tc_workspace_bytes(N, K);
-    if (!ctx->ws || ctx->ws_bytes < need)
-      return gcnb_fail(ctx, GCNB_E_WORKSPACE, "tcgen05 gemm needs %s%lld workspace bytes, have %lld", "",
-                       (long long)need, (long long)ctx->ws_bytes);
-    ldbt = ld32(K);
-    float* w = reinterpret_cast<float*>(ctx->ws);
-    int rc = transpose_into_ws(ctx, B, ldb, K, N, w, ldbt);
-    if (rc != GCNB_OK) return rc;
-    Bt = w;
-  }
-  if (!make_map(&p.mapA[0], A, M, K, lda, BM) || !make_map(&p.mapB[0], Bt, N, K, ldbt, p.BN))
+  // weights: N x K copy (transposed when B is stored K x N) plus its residual, both in the workspace
+  const size_t need = gcnb_gemm_tc_workspace_bytes(N, K);
+  if (!ctx->ws || ctx->ws_bytes < need)
+    return gcnb_fail(ctx, GCNB_E_WORKSPACE, "tcgen05 gemm needs %s%lld workspace bytes, have %lld", "",
+                     (long long)need, (long long)ctx->ws_bytes);
+  const int ldbt = ld32(K);
+  float* Bt = reinterpret_cast<float*>(ctx->ws);
+  float* Blo = Bt + (size_t)N * ldbt;
+  int rc = split_weights(ctx, B, ldb, K, N, transB ? 0 : 1, Bt, Blo, ldbt);
+  if (rc != GCNB_OK) return rc;
+  if (!make_map(&p.mapA[0], A, M, K, lda, BM) || !make_map(&p.mapB[0], Bt, N, K, ldbt, p.BN) ||
+      !make_map(&p.mapBlo[0], Blo, N, K, ldbt, p.BN))
+    return gcnb_fail(ctx, GCNB_E_CUDA, "cuTensorMapEncodeTiled failed%s", "");
+  if (!make_map(&p.mapOut[0], C, M, N, ldc, BM) || (accumulate && !make_map(&p.mapIn, C, M, N, ldc, BM)))
     return gcnb_fail(ctx, GCNB_E_CUDA, "cuTensorMapEncodeTiled failed%s", "");
   p.nphase = 1;
   p.kblocks[0] = cdiv(K, BK);
@@ -632,35 +732,45 @@ bool gcnb_highway_tc_supported(const gcnb_ctx* ctx, int n_rows, int hd, int lds,
   return encode_fn() != nullptr;
 }
 
-size_t gcnb_highway_tc_workspace_bytes(int hd) { return 2 * (size_t)hd * ld32(hd) * sizeof(float); }
+size_t gcnb_highway_tc_workspace_bytes(int hd) { return 4 * (size_t)hd * ld32(hd) * sizeof(float); }
 
 int gcnb_highway_tc(gcnb_ctx* ctx, int n_rows, int hd, const float* S, int lds, const float* X, int ldx,
                     const float* Wh, int ldwh, const float* bh, const float* Wt, int ldwt, const float* bt, int act,
                     float* Y, int ldy, float* H, int ldh, float* T, int ldt) {
-  GCNB_REQUIRE(ctx, aligned16(S) && aligned16(X) && aligned16(Y) && aligned16(Wh) && aligned16(Wt),
-               "tcgen05 highway: 16-byte aligned matrices");
+  GCNB_REQUIRE(ctx, aligned16(S) && aligned16(X) && aligned16(Y) && aligned16(Wh) && aligned16(Wt) &&
+                        (!H || aligned16(H)) && (!T || aligned16(T)) && (ldy % 4) == 0 && (!H || (ldh % 4) == 0) &&
+                        (!T || (ldt % 4) == 0),
+               "tcgen05 highway: 16-byte aligned matrices, leading dimensions multiple of 4");
   const size_t need = gcnb_highway_tc_workspace_bytes(hd);
   if (!ctx->ws || ctx->ws_bytes < need)
     return gcnb_fail(ctx, GCNB_E_WORKSPACE, "tcgen05 highway needs %s%lld workspace bytes, have %lld", "",
                      (long long)need, (long long)ctx->ws_bytes);
   const int ldw = ld32(hd);
+  const size_t wsz = (size_t)hd * ldw;
   float* WhT = reinterpret_cast<float*>(ctx->ws);
-  float* WtT = WhT + (size_t)hd * ldw;
-  int rc = transpose_into_ws(ctx, Wh, ldwh, hd, hd, WhT, ldw);
+  float* WhL = WhT + wsz;
+  float* WtT = WhL + wsz;
+  float* WtL = WtT + wsz;
+  int rc = split_weights(ctx, Wh, ldwh, hd, hd, 1, WhT, WhL, ldw);
   if (rc != GCNB_OK) return rc;
-  rc = transpose_into_ws(ctx, Wt, ldwt, hd, hd, WtT, ldw);
+  rc = split_weights(ctx, Wt, ldwt, hd, hd, 1, WtT, WtL, ldw);
   if (rc != GCNB_OK) return rc;
   TcParams p;
   memset(&p, 0, sizeof(p));
   pick_bn(hd, &p.BN, &p.n_tiles);
   if (!make_map(&p.mapA[0], S, n_rows, hd, lds, BM) || !make_map(&p.mapB[0], WhT, hd, hd, ldw, p.BN) ||
-      !make_map(&p.mapA[1], X, n_rows, hd, ldx, BM) || !make_map(&p.mapB[1], WtT, hd, hd, ldw, p.BN))
+      !make_map(&p.mapBlo[0], WhL, hd, hd, ldw, p.BN) || !make_map(&p.mapA[1], X, n_rows, hd, ldx, BM) ||
+      !make_map(&p.mapB[1], WtT, hd, hd, ldw, p.BN) || !make_map(&p.mapBlo[1], WtL, hd, hd, ldw, p.BN))
+    return gcnb_fail(ctx, GCNB_E_CUDA, "cuTensorMapEncodeTiled failed%s", "");
+  if (!make_map(&p.mapIn, X, n_rows, hd, ldx, BM) || !make_map(&p.mapOut[0], Y, n_rows, hd, ldy, BM) ||
+      (H && !make_map(&p.mapOut[1], H, n_rows, hd, ldh, BM)) || (T && !make_map(&p.mapOut[2], T, n_rows, hd, ldt, BM)))
     return gcnb_fail(ctx, GCNB_E_CUDA, "cuTensorMapEncodeTiled failed%s", "");
   p.nphase = 2;
   p.kblocks[0] = p.kblocks[1] = cdiv(hd, BK);
   p.M = n_rows; p.N = hd;
   p.C = Y; p.ldc = ldy; p.bias = bh; p.act = act; p.accumulate = 0;
   p.bias_t = bt; p.X = X; p.ldx = ldx; p.H = H; p.ldh = ldh; p.T = T; p.ldt = ldt;
+  p.dbg = reinterpret_cast<long long*>(ctx->tc_dbg);
   return launch(ctx, p);
 }
 
