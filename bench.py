@@ -170,7 +170,7 @@ def run_reference(args, cfg, wname):
                              "host_cpus": len(os.sched_getaffinity(0))},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -330,13 +330,27 @@ def run_gpu(args, cfg, wname):
                 "host_cpus": len(os.sched_getaffinity(0))}
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else this process (or NCCL, which prints its version
+    banner on stdout) writes lands on stderr, so stdout carries exactly one line."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
