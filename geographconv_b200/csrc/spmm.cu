@@ -398,7 +398,9 @@ int launch_pass(gcnb_ctx* ctx, const SpmmParams& p, int engine, int unroll) {
       int ctas_per_sm = (int)((220u * 1024u) / (smem + 1024));
       if (ctas_per_sm < 1) ctas_per_sm = 1;
       if (ctas_per_sm > 4) ctas_per_sm = 4;
-      int g = ctx->sm_count * ctas_per_sm;
+      int sms = ctx->sm_count - ctx->sm_margin;
+      if (sms < 1) sms = 1;
+      int g = sms * ctas_per_sm;
       if (g > grid) g = grid;
       kern<<<g, WARPS * 32, smem, ctx->stream>>>(p);
       GCNB_LAUNCHED(ctx);

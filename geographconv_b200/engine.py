@@ -36,7 +36,8 @@ import torch
 
 from . import capi
 from .capi import ACT, GcnbCsr, GcnbEpilogue
-from .partition import ParamLayout, ld_of, local_index_split, row_blocks, slice_rows, transpose_csr, is_symmetric
+from .partition import (ParamLayout, ld_of, local_index_split, row_blocks, slice_rows, transpose_csr, is_symmetric,
+                        split_by_exchange_chunk)
 
 SPMM_CHUNK_DEFAULT = 1024  # nonzeros per row item (rows longer than this are split; see gcnb_csr_plan)
 
@@ -122,10 +123,11 @@ class HostGraph:
     memory across epochs, gcnmain.py:172-179) and cached by the engine."""
 
     def __init__(self, X, A, world, rank, chunk, need_backward, assume_symmetric=None, hot_density=0.0,
-                 hot_max=0):
+                 hot_max=0, exchange_chunks=1):
         n = X.shape[0]
         self.n = n
-        self.n_pad, blocks = row_blocks(n, world)
+        self.exchange_chunks = exchange_chunks if world > 1 else 1
+        self.n_pad, blocks = row_blocks(n, world, self.exchange_chunks)
         self.r0, self.r1 = blocks[rank]
         self.n_loc = self.r1 - self.r0
         self.n_tot = self.n_pad * world if world > 1 else n
@@ -145,7 +147,8 @@ class HostGraph:
         self.X_hot = _pinned(X_hot.reshape(-1)) if self.kh else None
         self.hot_cols_p = _pinned(self.hot_cols) if self.kh else None
         self.X = HostCsr(Xl, chunk)  # the cold columns only when a hot block exists
-        self.A = HostCsr(Al, chunk)
+        # A_hat's row block, column-split into the pieces of the pipelined exchange (one piece on a single GPU)
+        self.A = [HostCsr(M, chunk) for M in split_by_exchange_chunk(Al, world, self.n_pad, self.exchange_chunks)]
         self.XT = self.AT = None
         self.symmetric = True
         if need_backward:
@@ -154,8 +157,10 @@ class HostGraph:
             if not self.symmetric:
                 # A^T.G for a row block needs rows r0:r1 of A^T
                 AT = transpose_csr(A)
-                self.AT = HostCsr(widen(slice_rows(AT, self.r0, self.r1)) if world > 1 else AT, chunk)
-        self.nbytes = sum(c.nbytes for c in (self.X, self.A, self.XT, self.AT) if c is not None)
+                ATl = widen(slice_rows(AT, self.r0, self.r1)) if world > 1 else AT
+                self.AT = [HostCsr(M, chunk) for M in
+                           split_by_exchange_chunk(ATl, world, self.n_pad, self.exchange_chunks)]
+        self.nbytes = sum(c.nbytes for c in [self.X, self.XT] + self.A + (self.AT or []) if c is not None)
         if self.kh:
             self.nbytes += self.X_hot.nbytes + self.hot_cols_p.nbytes
 
@@ -225,6 +230,12 @@ class Engine:
         self.group = group
         self.world = torch.distributed.get_world_size(group) if group is not None else 1
         self.rank = torch.distributed.get_rank(group) if group is not None else 0
+        # pipelined exchange (world > 1): the dense operand of every graph convolution is all-gathered in this many
+        # row pieces on a side stream while the SpMM consumes the pieces that already arrived
+        # (measured on C3, profiles/r1b_ncu.md: splitting the 32 nonzeros of a row over 4 pieces costs the SpMM more
+        # than the overlap wins, so the default is one piece; the exchange still runs on its own stream and overlaps
+        # the work that does not depend on it)
+        self.exchange_chunks = int(os.environ.get("GCNB_EXCHANGE_CHUNKS", "1")) if self.world > 1 else 1
         if device is None:
             device = torch.cuda.current_device()
         self.dev = torch.device("cuda", int(device))
@@ -232,7 +243,11 @@ class Engine:
         # one dedicated (non-default) stream carries every kernel, copy and collective of the engine;
         # torch allocations / fills happen on torch's current stream and are fenced by _fence()
         self.stream = torch.cuda.Stream(self.dev)
+        self.comm = torch.cuda.Stream(self.dev, priority=-1) if self.world > 1 else None
         self.ctx = capi.Context(int(device), C.c_void_p(self.stream.cuda_stream))
+        if self.world > 1 and self.exchange_chunks > 1:
+            # NCCL's kernels need SMs of their own next to the persistent SpMM CTAs they overlap with
+            self.ctx.set_option("sm_margin", int(os.environ.get("GCNB_SM_MARGIN", "16")))
         self.lib = self.ctx.lib
         L = layout
         self.params = torch.zeros(L.total, dtype=torch.float32, device=self.dev)
@@ -335,14 +350,14 @@ class Engine:
                 raise ValueError("A must be N x N with N = X.shape[0]")
             self.ctx.sync()
             hg = HostGraph(X, A, self.world, self.rank, self.spmm_chunk, need_backward, assume_symmetric,
-                           self.hot_density, self.hot_max)
+                           self.hot_density, self.hot_max, self.exchange_chunks)
             self.host = hg
             self.n, self.n_pad, self.r0, self.r1 = hg.n, hg.n_pad, hg.r0, hg.r1
             self.n_loc, self.n_tot, self.symmetric = hg.n_loc, hg.n_tot, hg.symmetric
             self.X = DeviceCsr(self, hg.X, capi.TAG_SPMM_X)
-            self.A = DeviceCsr(self, hg.A, capi.TAG_SPMM_A)
+            self.A = [DeviceCsr(self, h, capi.TAG_SPMM_A) for h in hg.A]
             self.XT = DeviceCsr(self, hg.XT, capi.TAG_SPMM_XT) if hg.XT is not None else None
-            self.AT = DeviceCsr(self, hg.AT, capi.TAG_SPMM_A) if hg.AT is not None else None
+            self.AT = [DeviceCsr(self, h, capi.TAG_SPMM_A) for h in hg.AT] if hg.AT is not None else None
             self.kh = hg.kh
             self.X_hot = self.hot_idx = None
             if hg.kh:
@@ -354,13 +369,15 @@ class Engine:
             self._idx_cache = {}
         else:
             hg = self.host
-            for d, h in ((self.X, hg.X), (self.A, hg.A), (self.XT, hg.XT), (self.AT, hg.AT)):
+            pairs = [(self.X, hg.X), (self.XT, hg.XT)] + list(zip(self.A, hg.A)) + \
+                (list(zip(self.AT, hg.AT)) if self.AT is not None else [])
+            for d, h in pairs:
                 if d is not None:
                     d.refill(self, h)
             if hg.kh:
                 self._upload_hot(hg)
-        self.A_out = self.A.retagged(capi.TAG_SPMM_A_NARROW)
-        self.AT_out = self.AT.retagged(capi.TAG_SPMM_A_NARROW) if self.AT is not None else None
+        self.A_out = [a.retagged(capi.TAG_SPMM_A_NARROW) for a in self.A]
+        self.AT_out = [a.retagged(capi.TAG_SPMM_A_NARROW) for a in self.AT] if self.AT is not None else None
         self.h2d_bytes_last_bind = hg.nbytes
 
     def _upload_hot(self, hg):
@@ -387,7 +404,10 @@ class Engine:
         self.S = self._zeros(n, maxld)  # A.x scratch (highway) / x.W scratch (plain, output)
         self.P = self._zeros(n, self.ldc)
         self.logits = self._zeros(n, self.ldc) if self.keep_logits else None
-        self.gath = self._zeros(self.n_tot, maxld) if self.world > 1 else None
+        self.gath = None
+        if self.world > 1:
+            cr = self.n_pad // self.exchange_chunks
+            self.gath = [self._zeros(self.world * cr, maxld) for _ in range(self.exchange_chunks)]
         if need_backward:
             self.G = self._zeros(n, self.ldc)
             self.U = self._zeros(n, maxld)
@@ -396,7 +416,8 @@ class Engine:
             self.dT = self._zeros(n, maxld)
         # workspace: the largest scratch any op of the step needs
         need = 1 << 20
-        need = max(need, self.lib.gcnb_spmm_workspace_bytes(C.byref(self.A.struct), max(widths + [L.output_size])))
+        for a in self.A + (self.AT or []):
+            need = max(need, self.lib.gcnb_spmm_workspace_bytes(C.byref(a.struct), max(widths + [L.output_size])))
         need = max(need, self.lib.gcnb_spmm_workspace_bytes(C.byref(self.X.struct), hd))
         need = max(need, self.lib.gcnb_highway_workspace_bytes(0, max(widths)))
         wall = max(widths + [L.output_size, hd])
@@ -409,9 +430,6 @@ class Engine:
                 need = max(need, self.lib.gcnb_gemm_workspace_bytes(1, self.kh, hd, max(n, 1)))
         if need_backward:
             need = max(need, self.lib.gcnb_spmm_workspace_bytes(C.byref(self.XT.struct), hd))
-            if self.AT is not None:
-                need = max(need, self.lib.gcnb_spmm_workspace_bytes(C.byref(self.AT.struct),
-                                                                    max(widths + [L.output_size])))
             wmax = max(widths + [L.output_size])
             need = max(need, self.lib.gcnb_gemm_workspace_bytes(1, wmax, wmax, max(n, 1)))
             need = max(need, self.lib.gcnb_colsum_workspace_bytes(n, wmax))
@@ -468,14 +486,52 @@ class Engine:
             return
         self.ctx.call("gcnb_gemm_f32", tA, tB, M, N, K, p(A), lda, p(B), ldb, p(Cm), ldc, accumulate, p(bias), act)
 
-    def _gathered(self, x, ld):
-        """Dense operand of an A-SpMM: the local block itself, or its all-gather over ranks."""
+    def _conv_begin(self, x):
+        """Start moving the dense operand ``x`` (n_pad x ld, this rank's rows) of a graph convolution to every rank:
+        ``exchange_chunks`` all-gathers on the side stream, one per row piece.  No-op on a single GPU."""
         if self.world == 1:
-            return x, x.shape[1]
-        out = self.gath.view(-1)[: self.n_tot * x.shape[1]].view(self.n_tot, x.shape[1])
-        with torch.cuda.stream(self.stream):
-            torch.distributed.all_gather_into_tensor(out, x, group=self.group)
-        return out, x.shape[1]
+            return x
+        ld = x.shape[1]
+        cr = self.n_pad // self.exchange_chunks
+        ready = torch.cuda.Event()
+        ready.record(self.stream)
+        self.comm.wait_event(ready)  # x is complete; the previous consumers of the gather buffers are done
+        handle = []
+        with torch.cuda.stream(self.comm):
+            for c in range(self.exchange_chunks):
+                dst = self.gath[c].view(-1)[: self.world * cr * ld].view(self.world * cr, ld)
+                torch.distributed.all_gather_into_tensor(dst, x[c * cr:(c + 1) * cr], group=self.group)
+                ev = torch.cuda.Event()
+                ev.record(self.comm)
+                handle.append((dst, ev))
+        return handle
+
+    def _conv_finish(self, handle, parts, out, ldo, K, bias=None, act=0, softmax=0, logits=None):
+        """out = epilogue(A_hat . operand): one SpMM per arrived piece; the pieces accumulate into ``out`` and the
+        bias / activation / softmax epilogue runs with the last one."""
+        if self.world == 1:
+            x = handle
+            self._spmm(parts[0], x, x.shape[1], out, ldo, K, bias=bias, act=act, softmax=softmax, logits=logits)
+            return
+        last = len(handle) - 1
+        for c, (dst, ev) in enumerate(handle):
+            self.stream.wait_event(ev)
+            if last == 0:
+                self._spmm(parts[c], dst, dst.shape[1], out, ldo, K, bias=bias, act=act, softmax=softmax, logits=logits)
+            elif c < last:
+                self._spmm(parts[c], dst, dst.shape[1], out, ldo, K, accumulate=0 if c == 0 else 1)
+            else:
+                self._spmm(parts[c], dst, dst.shape[1], out, ldo, K, bias=bias, act=act, softmax=softmax, logits=logits,
+                           accumulate=2)
+
+    def _conv(self, x, parts, out, ldo, K, **epi):
+        self._conv_finish(self._conv_begin(x), parts, out, ldo, K, **epi)
+
+    def conv_touched_bytes(self, K):
+        """B_touch of one A_hat . H product of this rank (all exchange pieces together)."""
+        nnz = sum(a.nnz for a in self.A)
+        rows = self.A[0].shape[0]
+        return nnz * 8 + (rows + 1) * 4 + nnz * K * 4 + rows * K * 4
 
     # ------------------------------------------------------------------ forward
     def forward(self, train=False, seed=0, want_gates=False):
@@ -504,9 +560,8 @@ class Engine:
                 bh, _ = self._pptr("bh%d" % k)
                 Wt, ldwt = self._pptr("Wt%d" % k)
                 bt, _ = self._pptr("bt%d" % k)
-                xg, ldg = self._gathered(x, ldx)
                 S = self.S.view(-1)[: self.nbuf * ldx].view(self.nbuf, ldx)
-                self._spmm(self.A, xg, ldg, S, ldx, width)
+                self._conv(x, self.A, S, ldx, width)
                 self.ctx.call("gcnb_highway_fwd_f32", n, width, _ptr(S), ldx, _ptr(x), ldx, Wh, ldwh, bh, Wt, ldwt,
                               bt, self.act, _ptr(b["Y"]), ldy, _ptr(b["H"]), ldy, _ptr(b["T"]), ldy)
             else:
@@ -517,8 +572,7 @@ class Engine:
                 # reference order (gcnmodel.py:126-133): dense product first, then A, then bias
                 Q = self.S.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
                 self._gemm(0, 0, n, n_out, width, x, ldx, W, ldw, Q, ldy)
-                qg, ldg = self._gathered(Q, ldy)
-                self._spmm(self.A, qg, ldg, b["Y"], ldy, n_out, bias=bb, act=self.act)
+                self._conv(Q, self.A, b["Y"], ldy, n_out, bias=bb, act=self.act)
                 width = n_out
             x, ldx = b["Y"], ldy
         self.x_last, self.ld_last, self.w_last = x, ldx, width
@@ -527,8 +581,7 @@ class Engine:
         Cn = L.output_size
         Q = self.S.view(-1)[: self.nbuf * self.ldc].view(self.nbuf, self.ldc)
         self._gemm(0, 0, n, Cn, width, x, ldx, Wout, ldwo, Q, self.ldc)
-        qg, ldg = self._gathered(Q, self.ldc)
-        self._spmm(self.A_out, qg, ldg, self.P, self.ldc, Cn, bias=bout, softmax=1, logits=self.logits)
+        self._conv(Q, self.A_out, self.P, self.ldc, Cn, bias=bout, softmax=1, logits=self.logits)
         return self.P
 
     # ------------------------------------------------------------------ backward + Adam
@@ -539,15 +592,15 @@ class Engine:
         csrT = self.A if self.AT is None else self.AT
         self.ctx.call("gcnb_xent_grad_f32", _ptr(self.P), self.ldc, Cn, self.nbuf, _ptr(d_idx), _ptr(d_lab),
                       n_idx_local, 1.0 / float(n_train_global), _ptr(self.G), self.ldc)
-        gg, ldg = self._gathered(self.G, self.ldc)
         U = self.U.view(-1)[: self.nbuf * self.ldc].view(self.nbuf, self.ldc)
-        self._spmm(self.A_out if self.AT is None else self.AT_out, gg, ldg, U, self.ldc, Cn)
+        pending = self._conv_begin(self.G)
         x, ldx, width = self.x_last, self.ld_last, self.w_last
-        gW, ldgw = self._gptr("Wout")
         gb, _ = self._gptr("bout")
+        self.ctx.call("gcnb_colsum_f32", n, Cn, _ptr(self.G), self.ldc, gb, 0)  # dbout (overlaps the exchange)
+        self._conv_finish(pending, self.A_out if self.AT is None else self.AT_out, U, self.ldc, Cn)
+        gW, ldgw = self._gptr("Wout")
         Wout, ldwo = self._pptr("Wout")
         self._gemm(1, 0, width, Cn, n, x, ldx, U, self.ldc, gW, ldgw)          # dWout = x^T.U
-        self.ctx.call("gcnb_colsum_f32", n, Cn, _ptr(self.G), self.ldc, gb, 0)  # dbout
         dX = self.dX.view(-1)[: self.nbuf * ldx].view(self.nbuf, ldx)
         self._gemm(0, 1, n, width, Cn, U, self.ldc, Wout, ldwo, dX, ldx)        # dx = U.Wout^T
         for i in reversed(range(len(L.layers))):
@@ -564,32 +617,33 @@ class Engine:
                 # dHpre, dTpre, dx*(1-t) (in place over dX)
                 self.ctx.call("gcnb_highway_bwd_f32", n, n_out, ldy, _ptr(dX), _ptr(xin), _ptr(b["H"]), _ptr(b["T"]),
                               self.act, _ptr(dH), _ptr(dT), _ptr(dX))
-                hg, ldg = self._gathered(dH, ldy)
+                pending = self._conv_begin(dH)
                 V = self.U.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
-                self._spmm(csrT, hg, ldg, V, ldy, n_out)                            # V = A^T.dHpre
                 gWh, ldgh = self._gptr("Wh%d" % k)
                 gbh, _ = self._gptr("bh%d" % k)
                 gWt, ldgt = self._gptr("Wt%d" % k)
                 gbt, _ = self._gptr("bt%d" % k)
                 Wh, ldwh = self._pptr("Wh%d" % k)
                 Wt, ldwt = self._pptr("Wt%d" % k)
-                self._gemm(1, 0, n_in, n_out, n, xin, ldin, V, ldy, gWh, ldgh)      # dWh = x^T.V
+                # everything that does not need V = A^T.dHpre runs while its operand is being exchanged
                 self.ctx.call("gcnb_colsum_f32", n, n_out, _ptr(dH), ldy, gbh, 0)
-                self._gemm(0, 1, n, n_in, n_out, V, ldy, Wh, ldwh, dX, ldin, accumulate=1)   # dx += V.Wh^T
                 self._gemm(1, 0, n_in, n_out, n, xin, ldin, dT, ldy, gWt, ldgt)     # dWt = x^T.dTpre
                 self.ctx.call("gcnb_colsum_f32", n, n_out, _ptr(dT), ldy, gbt, 0)
                 self._gemm(0, 1, n, n_in, n_out, dT, ldy, Wt, ldwt, dX, ldin, accumulate=1)  # dx += dTpre.Wt^T
+                self._conv_finish(pending, csrT, V, ldy, n_out)                     # V = A^T.dHpre
+                self._gemm(1, 0, n_in, n_out, n, xin, ldin, V, ldy, gWh, ldgh)      # dWh = x^T.V
+                self._gemm(0, 1, n, n_in, n_out, V, ldy, Wh, ldwh, dX, ldin, accumulate=1)   # dx += V.Wh^T
             else:
                 dP = self.dH.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
                 self.ctx.call("gcnb_act_bwd_f32", n, n_out, ldy, _ptr(dX), _ptr(b["Y"]), self.act, 0.0, 0, 0, _ptr(dP))
-                pg, ldg = self._gathered(dP, ldy)
+                pending = self._conv_begin(dP)
                 V = self.U.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
-                self._spmm(csrT, pg, ldg, V, ldy, n_out)
-                gW, ldgw = self._gptr("W%d" % k)
                 gb, _ = self._gptr("b%d" % k)
+                self.ctx.call("gcnb_colsum_f32", n, n_out, _ptr(dP), ldy, gb, 0)
+                self._conv_finish(pending, csrT, V, ldy, n_out)
+                gW, ldgw = self._gptr("W%d" % k)
                 W, ldw = self._pptr("W%d" % k)
                 self._gemm(1, 0, n_in, n_out, n, xin, ldin, V, ldy, gW, ldgw)
-                self.ctx.call("gcnb_colsum_f32", n, n_out, _ptr(dP), ldy, gb, 0)
                 dXn = self.dX.view(-1)[: self.nbuf * ldin].view(self.nbuf, ldin)
                 self._gemm(0, 1, n, n_in, n_out, V, ldy, W, ldw, dXn, ldin)
                 dX = dXn

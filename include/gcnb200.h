@@ -69,7 +69,8 @@ void* gcnb_get_stream(const gcnb_ctx* ctx);
 int gcnb_set_workspace(gcnb_ctx* ctx, void* dev_ptr, size_t bytes);
 /* named integer options: "spmm_variant" (0 = LDG.128 register gather, 1 = bulk-copy/TMA staged),
  * "spmm_unroll" (nonzeros gathered per batch), "gemm_tc" (1 = tcgen05 path where supported, the
- * default), "tc_launches" (read-only count of tcgen05 kernels launched). */
+ * default), "tc_launches" (read-only count of tcgen05 kernels launched), "sm_margin" (SMs the persistent
+ * SpMM kernel leaves to concurrently running collectives). */
 int gcnb_set_option(gcnb_ctx* ctx, const char* name, int value);
 int gcnb_get_option(const gcnb_ctx* ctx, const char* name, int* value);
 int gcnb_sync(gcnb_ctx* ctx);

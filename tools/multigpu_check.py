@@ -5,8 +5,7 @@
         tools/multigpu_check.py
 
 Every rank passes the same full X / A / indices to GraphConv (shard=True).  Rank 0 compares predict and one
-training step with (a) the NumPy oracle and (b) a single-GPU run of the same library: the forward must be
-bit-identical (each output row is reduced in the same order whichever rank owns it).
+training step with (a) the NumPy oracle and (b) a single-GPU run of the same library (equal to fp32 rounding).
 """
 import os
 import sys
@@ -45,7 +44,9 @@ def main():
             one = GraphConv(cfg["f"], cfg["classes"], hid, 0.0, 0.5, highway=highway, device=local, shard=False)
             one.build_model(A, seed=3)
             p1, pr1 = one.predict(X, A, te)
-            same = np.array_equal(pr1, probs) and np.array_equal(p1, preds)
+            # each rank picks the hot columns of ITS rows and may split the exchange into pieces, so row sums are
+            # associated differently than on one GPU: equal to fp32 rounding, not bit for bit
+            same = np.allclose(pr1, probs, rtol=2e-5, atol=1e-8) and (p1 == preds).mean() > 0.999
             out1 = one.f_train(X, Y[tr], Y[dev], A, tr, dev, seed=seed, update=False)
             g1 = one._get_engine().get_grads()
             rp, rprob = gcn_ref.predict(params, X, A, te, hid, highway)
@@ -58,7 +59,7 @@ def main():
             for g, rg, gs in zip(grads, r["grads"], g1):
                 np.testing.assert_allclose(g, rg, rtol=1e-3, atol=1e-4 * float(np.abs(rg).max()) + 1e-12)
                 np.testing.assert_allclose(g, gs, rtol=1e-4, atol=1e-5 * float(np.abs(gs).max()) + 1e-12)
-            print("world=%d highway=%s: forward bit-identical to 1 GPU: %s; oracle parity ok; loss %.6f vs 1-GPU %.6f"
+            print("world=%d highway=%s: forward matches 1 GPU to fp32 rounding: %s; oracle parity ok; loss %.6f vs 1-GPU %.6f"
                   % (world, highway, same, out[0], out1[0]), flush=True)
             ok = ok and same
     dist.barrier()
