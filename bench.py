@@ -257,7 +257,7 @@ def run_gpu(args, cfg, wname):
     spmm_ms, spmm_ops = prof["spmm_a"]
     peak, peak_kind = load_peaks()
     b_touch = eng.conv_touched_bytes(hd)
-    pieces = len(eng.A)  # SpMM launches per graph convolution (pipelined exchange pieces)
+    pieces = len(eng._panels(hd, eng.ldh[0], False)) if world > 1 else 1  # SpMM launches per graph convolution
     roof = None
     traffic = args.ncu_traffic_bytes
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")

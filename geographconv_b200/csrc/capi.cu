@@ -193,6 +193,17 @@ extern "C" int gcnb_memset(gcnb_ctx* ctx, void* dst_dev, int byte, size_t bytes)
   return GCNB_OK;
 }
 
+extern "C" int gcnb_copy2d_f32(gcnb_ctx* ctx, const float* src, int32_t ld_src, float* dst, int32_t ld_dst,
+                               int32_t rows, int32_t cols) {
+  if (!ctx) return GCNB_E_INVALID;
+  if (rows == 0 || cols == 0) return GCNB_OK;
+  GCNB_REQUIRE(ctx, src && dst && ld_src >= cols && ld_dst >= cols, "bad 2-D copy");
+  ProfScope scope(ctx, GCNB_TAG_COPY);
+  GCNB_CUDA(ctx, cudaMemcpy2DAsync(dst, (size_t)ld_dst * sizeof(float), src, (size_t)ld_src * sizeof(float),
+                                   (size_t)cols * sizeof(float), (size_t)rows, cudaMemcpyDeviceToDevice, ctx->stream));
+  return GCNB_OK;
+}
+
 // ------------------------------------------------------------------------------- dense ops
 extern "C" int gcnb_gemm_f32(gcnb_ctx* ctx, int32_t transA, int32_t transB, int32_t M, int32_t N, int32_t K,
                              const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc,

@@ -36,8 +36,7 @@ import torch
 
 from . import capi
 from .capi import ACT, GcnbCsr, GcnbEpilogue
-from .partition import (ParamLayout, ld_of, local_index_split, row_blocks, slice_rows, transpose_csr, is_symmetric,
-                        split_by_exchange_chunk)
+from .partition import ParamLayout, ld_of, local_index_split, row_blocks, slice_rows, transpose_csr, is_symmetric
 
 SPMM_CHUNK_DEFAULT = 1024  # nonzeros per row item (rows longer than this are split; see gcnb_csr_plan)
 
@@ -123,11 +122,10 @@ class HostGraph:
     memory across epochs, gcnmain.py:172-179) and cached by the engine."""
 
     def __init__(self, X, A, world, rank, chunk, need_backward, assume_symmetric=None, hot_density=0.0,
-                 hot_max=0, exchange_chunks=1):
+                 hot_max=0):
         n = X.shape[0]
         self.n = n
-        self.exchange_chunks = exchange_chunks if world > 1 else 1
-        self.n_pad, blocks = row_blocks(n, world, self.exchange_chunks)
+        self.n_pad, blocks = row_blocks(n, world)
         self.r0, self.r1 = blocks[rank]
         self.n_loc = self.r1 - self.r0
         self.n_tot = self.n_pad * world if world > 1 else n
@@ -147,8 +145,7 @@ class HostGraph:
         self.X_hot = _pinned(X_hot.reshape(-1)) if self.kh else None
         self.hot_cols_p = _pinned(self.hot_cols) if self.kh else None
         self.X = HostCsr(Xl, chunk)  # the cold columns only when a hot block exists
-        # A_hat's row block, column-split into the pieces of the pipelined exchange (one piece on a single GPU)
-        self.A = [HostCsr(M, chunk) for M in split_by_exchange_chunk(Al, world, self.n_pad, self.exchange_chunks)]
+        self.A = HostCsr(Al, chunk)
         self.XT = self.AT = None
         self.symmetric = True
         if need_backward:
@@ -158,9 +155,8 @@ class HostGraph:
                 # A^T.G for a row block needs rows r0:r1 of A^T
                 AT = transpose_csr(A)
                 ATl = widen(slice_rows(AT, self.r0, self.r1)) if world > 1 else AT
-                self.AT = [HostCsr(M, chunk) for M in
-                           split_by_exchange_chunk(ATl, world, self.n_pad, self.exchange_chunks)]
-        self.nbytes = sum(c.nbytes for c in [self.X, self.XT] + self.A + (self.AT or []) if c is not None)
+                self.AT = HostCsr(ATl, chunk)
+        self.nbytes = sum(c.nbytes for c in (self.X, self.XT, self.A, self.AT) if c is not None)
         if self.kh:
             self.nbytes += self.X_hot.nbytes + self.hot_cols_p.nbytes
 
@@ -226,16 +222,17 @@ class Engine:
         self.keep_logits = keep_logits
         # dense hot-column block of X (split_hot_columns): columns at least this dense, at most hot_max of them
         self.hot_density = float(os.environ.get("GCNB_HOT_DENSITY", "0.05") if hot_density is None else hot_density)
-        self.hot_max = int(os.environ.get("GCNB_HOT_MAX", "512") if hot_max is None else hot_max)
+        self.hot_max = int(os.environ.get("GCNB_HOT_MAX", "1024") if hot_max is None else hot_max)
         self.group = group
         self.world = torch.distributed.get_world_size(group) if group is not None else 1
         self.rank = torch.distributed.get_rank(group) if group is not None else 0
-        # pipelined exchange (world > 1): the dense operand of every graph convolution is all-gathered in this many
-        # row pieces on a side stream while the SpMM consumes the pieces that already arrived
-        # (measured on C3, profiles/r1b_ncu.md: splitting the 32 nonzeros of a row over 4 pieces costs the SpMM more
-        # than the overlap wins, so the default is one piece; the exchange still runs on its own stream and overlaps
-        # the work that does not depend on it)
-        self.exchange_chunks = int(os.environ.get("GCNB_EXCHANGE_CHUNKS", "1")) if self.world > 1 else 1
+        # pipelined exchange (world > 1): the dense operand of a graph convolution travels in column panels of this
+        # many floats; panel c+1 is all-gathered on a side stream while the SpMM already multiplies panel c (each
+        # nonzero still gathers one contiguous panel row, output panels are disjoint: no extra passes).  0 = one piece.
+        # Measured on C3 with 2 GPUs (profiles/r1b_multigpu.md): the narrower SpMMs and the packing copies cost more
+        # than the hidden exchange saves, so the default is one piece; the exchange still runs on its own stream and
+        # overlaps the backward work that does not depend on it.
+        self.exchange_panel = int(os.environ.get("GCNB_EXCHANGE_PANEL", "0")) if self.world > 1 else 0
         if device is None:
             device = torch.cuda.current_device()
         self.dev = torch.device("cuda", int(device))
@@ -245,9 +242,9 @@ class Engine:
         self.stream = torch.cuda.Stream(self.dev)
         self.comm = torch.cuda.Stream(self.dev, priority=-1) if self.world > 1 else None
         self.ctx = capi.Context(int(device), C.c_void_p(self.stream.cuda_stream))
-        if self.world > 1 and self.exchange_chunks > 1:
-            # NCCL's kernels need SMs of their own next to the persistent SpMM CTAs they overlap with
-            self.ctx.set_option("sm_margin", int(os.environ.get("GCNB_SM_MARGIN", "16")))
+        if self.world > 1 and "GCNB_SM_MARGIN" in os.environ:
+            # SMs the persistent SpMM kernel leaves to concurrently running NCCL kernels
+            self.ctx.set_option("sm_margin", int(os.environ["GCNB_SM_MARGIN"]))
         self.lib = self.ctx.lib
         L = layout
         self.params = torch.zeros(L.total, dtype=torch.float32, device=self.dev)
@@ -350,14 +347,14 @@ class Engine:
                 raise ValueError("A must be N x N with N = X.shape[0]")
             self.ctx.sync()
             hg = HostGraph(X, A, self.world, self.rank, self.spmm_chunk, need_backward, assume_symmetric,
-                           self.hot_density, self.hot_max, self.exchange_chunks)
+                           self.hot_density, self.hot_max)
             self.host = hg
             self.n, self.n_pad, self.r0, self.r1 = hg.n, hg.n_pad, hg.r0, hg.r1
             self.n_loc, self.n_tot, self.symmetric = hg.n_loc, hg.n_tot, hg.symmetric
             self.X = DeviceCsr(self, hg.X, capi.TAG_SPMM_X)
-            self.A = [DeviceCsr(self, h, capi.TAG_SPMM_A) for h in hg.A]
+            self.A = DeviceCsr(self, hg.A, capi.TAG_SPMM_A)
             self.XT = DeviceCsr(self, hg.XT, capi.TAG_SPMM_XT) if hg.XT is not None else None
-            self.AT = [DeviceCsr(self, h, capi.TAG_SPMM_A) for h in hg.AT] if hg.AT is not None else None
+            self.AT = DeviceCsr(self, hg.AT, capi.TAG_SPMM_A) if hg.AT is not None else None
             self.kh = hg.kh
             self.X_hot = self.hot_idx = None
             if hg.kh:
@@ -369,15 +366,13 @@ class Engine:
             self._idx_cache = {}
         else:
             hg = self.host
-            pairs = [(self.X, hg.X), (self.XT, hg.XT)] + list(zip(self.A, hg.A)) + \
-                (list(zip(self.AT, hg.AT)) if self.AT is not None else [])
-            for d, h in pairs:
+            for d, h in ((self.X, hg.X), (self.XT, hg.XT), (self.A, hg.A), (self.AT, hg.AT)):
                 if d is not None:
                     d.refill(self, h)
             if hg.kh:
                 self._upload_hot(hg)
-        self.A_out = [a.retagged(capi.TAG_SPMM_A_NARROW) for a in self.A]
-        self.AT_out = [a.retagged(capi.TAG_SPMM_A_NARROW) for a in self.AT] if self.AT is not None else None
+        self.A_out = self.A.retagged(capi.TAG_SPMM_A_NARROW)
+        self.AT_out = self.AT.retagged(capi.TAG_SPMM_A_NARROW) if self.AT is not None else None
         self.h2d_bytes_last_bind = hg.nbytes
 
     def _upload_hot(self, hg):
@@ -404,10 +399,10 @@ class Engine:
         self.S = self._zeros(n, maxld)  # A.x scratch (highway) / x.W scratch (plain, output)
         self.P = self._zeros(n, self.ldc)
         self.logits = self._zeros(n, self.ldc) if self.keep_logits else None
-        self.gath = None
+        self.gath = self.pack = None
         if self.world > 1:
-            cr = self.n_pad // self.exchange_chunks
-            self.gath = [self._zeros(self.world * cr, maxld) for _ in range(self.exchange_chunks)]
+            self.gath = self._zeros(self.n_tot, maxld)   # gathered panels, laid out one after the other
+            self.pack = self._zeros(n, maxld)            # this rank's panels made contiguous for the collective
         if need_backward:
             self.G = self._zeros(n, self.ldc)
             self.U = self._zeros(n, maxld)
@@ -416,8 +411,9 @@ class Engine:
             self.dT = self._zeros(n, maxld)
         # workspace: the largest scratch any op of the step needs
         need = 1 << 20
-        for a in self.A + (self.AT or []):
-            need = max(need, self.lib.gcnb_spmm_workspace_bytes(C.byref(a.struct), max(widths + [L.output_size])))
+        for a in (self.A, self.AT):
+            if a is not None:
+                need = max(need, self.lib.gcnb_spmm_workspace_bytes(C.byref(a.struct), max(widths + [L.output_size])))
         need = max(need, self.lib.gcnb_spmm_workspace_bytes(C.byref(self.X.struct), hd))
         need = max(need, self.lib.gcnb_highway_workspace_bytes(0, max(widths)))
         wall = max(widths + [L.output_size, hd])
@@ -486,52 +482,64 @@ class Engine:
             return
         self.ctx.call("gcnb_gemm_f32", tA, tB, M, N, K, p(A), lda, p(B), ldb, p(Cm), ldc, accumulate, p(bias), act)
 
-    def _conv_begin(self, x):
+    def _panels(self, K, ld, whole):
+        """Column panels (first column, width in floats, valid columns) an operand of K columns travels in."""
+        w = self.exchange_panel
+        if whole or w <= 0 or w >= ld:
+            return [(0, ld, K)]
+        return [(c0, min(w, ld - c0), min(K - c0, min(w, ld - c0))) for c0 in range(0, ld, w) if c0 < K]
+
+    def _conv_begin(self, x, K, whole=False):
         """Start moving the dense operand ``x`` (n_pad x ld, this rank's rows) of a graph convolution to every rank:
-        ``exchange_chunks`` all-gathers on the side stream, one per row piece.  No-op on a single GPU."""
+        one all-gather per column panel on the side stream.  No-op on a single GPU."""
         if self.world == 1:
             return x
         ld = x.shape[1]
-        cr = self.n_pad // self.exchange_chunks
+        panels = self._panels(K, ld, whole)
+        srcs = []
+        off = 0
+        for c0, w, _ in panels:
+            if len(panels) == 1:
+                src = x
+            else:  # make the panel contiguous
+                src = self.pack.view(-1)[off * self.nbuf:(off + w) * self.nbuf].view(self.nbuf, w)
+                self.ctx.call("gcnb_copy2d_f32", C.c_void_p(x.data_ptr() + 4 * c0), ld, _ptr(src), w, self.nbuf, w)
+            srcs.append(src)
+            off += w
         ready = torch.cuda.Event()
         ready.record(self.stream)
-        self.comm.wait_event(ready)  # x is complete; the previous consumers of the gather buffers are done
+        self.comm.wait_event(ready)  # operand complete; earlier consumers of the gather buffers are done
         handle = []
+        off = 0
         with torch.cuda.stream(self.comm):
-            for c in range(self.exchange_chunks):
-                dst = self.gath[c].view(-1)[: self.world * cr * ld].view(self.world * cr, ld)
-                torch.distributed.all_gather_into_tensor(dst, x[c * cr:(c + 1) * cr], group=self.group)
+            for (c0, w, kc), src in zip(panels, srcs):
+                dst = self.gath.view(-1)[off * self.n_tot:(off + w) * self.n_tot].view(self.n_tot, w)
+                torch.distributed.all_gather_into_tensor(dst, src, group=self.group)
                 ev = torch.cuda.Event()
                 ev.record(self.comm)
-                handle.append((dst, ev))
+                handle.append((dst, ev, c0, w, kc))
+                off += w
         return handle
 
-    def _conv_finish(self, handle, parts, out, ldo, K, bias=None, act=0, softmax=0, logits=None):
-        """out = epilogue(A_hat . operand): one SpMM per arrived piece; the pieces accumulate into ``out`` and the
-        bias / activation / softmax epilogue runs with the last one."""
+    def _conv_finish(self, handle, csr, out, ldo, K, bias=None, act=0, softmax=0, logits=None):
+        """out = epilogue(A_hat . operand): one SpMM per arrived column panel, each writing its own output columns."""
         if self.world == 1:
             x = handle
-            self._spmm(parts[0], x, x.shape[1], out, ldo, K, bias=bias, act=act, softmax=softmax, logits=logits)
+            self._spmm(csr, x, x.shape[1], out, ldo, K, bias=bias, act=act, softmax=softmax, logits=logits)
             return
-        last = len(handle) - 1
-        for c, (dst, ev) in enumerate(handle):
+        for dst, ev, c0, w, kc in handle:
             self.stream.wait_event(ev)
-            if last == 0:
-                self._spmm(parts[c], dst, dst.shape[1], out, ldo, K, bias=bias, act=act, softmax=softmax, logits=logits)
-            elif c < last:
-                self._spmm(parts[c], dst, dst.shape[1], out, ldo, K, accumulate=0 if c == 0 else 1)
-            else:
-                self._spmm(parts[c], dst, dst.shape[1], out, ldo, K, bias=bias, act=act, softmax=softmax, logits=logits,
-                           accumulate=2)
+            b = None if bias is None else C.c_void_p(bias.value + 4 * c0)
+            self._spmm(csr, dst, w, C.c_void_p(out.data_ptr() + 4 * c0), ldo, kc, bias=b, act=act, softmax=softmax,
+                       logits=logits)
 
-    def _conv(self, x, parts, out, ldo, K, **epi):
-        self._conv_finish(self._conv_begin(x), parts, out, ldo, K, **epi)
+    def _conv(self, x, csr, out, ldo, K, **epi):
+        whole = bool(epi.get("softmax"))  # a row softmax needs every column of the row in one pass
+        self._conv_finish(self._conv_begin(x, K, whole), csr, out, ldo, K, **epi)
 
     def conv_touched_bytes(self, K):
-        """B_touch of one A_hat . H product of this rank (all exchange pieces together)."""
-        nnz = sum(a.nnz for a in self.A)
-        rows = self.A[0].shape[0]
-        return nnz * 8 + (rows + 1) * 4 + nnz * K * 4 + rows * K * 4
+        """B_touch of one A_hat . H product of this rank."""
+        return self.A.touched_bytes(K)
 
     # ------------------------------------------------------------------ forward
     def forward(self, train=False, seed=0, want_gates=False):
@@ -593,7 +601,7 @@ class Engine:
         self.ctx.call("gcnb_xent_grad_f32", _ptr(self.P), self.ldc, Cn, self.nbuf, _ptr(d_idx), _ptr(d_lab),
                       n_idx_local, 1.0 / float(n_train_global), _ptr(self.G), self.ldc)
         U = self.U.view(-1)[: self.nbuf * self.ldc].view(self.nbuf, self.ldc)
-        pending = self._conv_begin(self.G)
+        pending = self._conv_begin(self.G, Cn)
         x, ldx, width = self.x_last, self.ld_last, self.w_last
         gb, _ = self._gptr("bout")
         self.ctx.call("gcnb_colsum_f32", n, Cn, _ptr(self.G), self.ldc, gb, 0)  # dbout (overlaps the exchange)
@@ -617,7 +625,7 @@ class Engine:
                 # dHpre, dTpre, dx*(1-t) (in place over dX)
                 self.ctx.call("gcnb_highway_bwd_f32", n, n_out, ldy, _ptr(dX), _ptr(xin), _ptr(b["H"]), _ptr(b["T"]),
                               self.act, _ptr(dH), _ptr(dT), _ptr(dX))
-                pending = self._conv_begin(dH)
+                pending = self._conv_begin(dH, n_out)
                 V = self.U.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
                 gWh, ldgh = self._gptr("Wh%d" % k)
                 gbh, _ = self._gptr("bh%d" % k)
@@ -636,7 +644,7 @@ class Engine:
             else:
                 dP = self.dH.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
                 self.ctx.call("gcnb_act_bwd_f32", n, n_out, ldy, _ptr(dX), _ptr(b["Y"]), self.act, 0.0, 0, 0, _ptr(dP))
-                pending = self._conv_begin(dP)
+                pending = self._conv_begin(dP, n_out)
                 V = self.U.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
                 gb, _ = self._gptr("b%d" % k)
                 self.ctx.call("gcnb_colsum_f32", n, n_out, _ptr(dP), ldy, gb, 0)

@@ -112,45 +112,14 @@ class ParamLayout:
 # 1-D row partition
 # ------------------------------------------------------------------------------------------
 
-def row_blocks(n, world, align=1):
+def row_blocks(n, world):
     """Contiguous equal blocks: rank p owns rows [p*n_pad, min(n, (p+1)*n_pad)).
 
     Equal (padded) block size keeps the all-gather a single fixed-size collective and makes the
     gathered row index equal the global node id, so column indices of A need no remapping.
-    ``align``: n_pad is rounded up to a multiple of it (the number of pipeline chunks of the exchange).
     """
     n_pad = (n + world - 1) // world
-    n_pad = (n_pad + align - 1) // align * align
     return n_pad, [(min(n, p * n_pad), min(n, (p + 1) * n_pad)) for p in range(world)]
-
-
-def split_by_exchange_chunk(Al, world, n_pad, chunks):
-    """Column-split the local row block ``Al`` (n_loc x world*n_pad) for the pipelined exchange.
-
-    The dense operand is all-gathered in ``chunks`` pieces: piece c holds rows [c*cr, (c+1)*cr) of every rank's
-    block (cr = n_pad / chunks) laid out rank-major, i.e. global row j = p*n_pad + o sits at row p*cr + (o - c*cr)
-    of piece c = o // cr.  Returns one CSR per piece with the column ids rewritten to that layout; with
-    ``chunks == 1`` this is the identity.
-    """
-    Al = Al.tocsr()
-    if chunks == 1:
-        return [Al]
-    cr = n_pad // chunks
-    cols = Al.indices.astype(np.int64)
-    p, o = cols // n_pad, cols % n_pad
-    piece = o // cr
-    new_col = (p * cr + (o - piece * cr)).astype(np.int32)
-    rows = np.repeat(np.arange(Al.shape[0], dtype=np.int32), np.diff(Al.indptr))
-    out = []
-    for c in range(chunks):
-        m = piece == c
-        counts = np.bincount(rows[m], minlength=Al.shape[0])
-        indptr = np.zeros(Al.shape[0] + 1, dtype=np.int32)
-        np.cumsum(counts, out=indptr[1:])
-        M = sp.csr_matrix((Al.data[m], new_col[m], indptr), shape=(Al.shape[0], world * cr))
-        M.sort_indices()
-        out.append(M)
-    return out
 
 
 def slice_rows(M, r0, r1):

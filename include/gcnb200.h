@@ -87,6 +87,10 @@ int gcnb_prof_collect(gcnb_ctx* ctx, float* ms, long long* ops);
 int gcnb_h2d(gcnb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int gcnb_d2h(gcnb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 int gcnb_memset(gcnb_ctx* ctx, void* dst_dev, int byte, size_t bytes);
+/* device-to-device copy of a rows x cols fp32 block between matrices with different leading dimensions (a column
+ * panel of an activation made contiguous for the all-gather of the row-partitioned exchange) */
+int gcnb_copy2d_f32(gcnb_ctx* ctx, const float* src, int32_t ld_src, float* dst, int32_t ld_dst, int32_t rows,
+                    int32_t cols);
 
 /* ---------------------------------------------------------------- CSR ----------------- */
 /* A CSR matrix resident in device memory plus its work decomposition ("plan"): every row is
