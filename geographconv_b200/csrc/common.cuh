@@ -30,6 +30,7 @@ struct gcnb_ctx {
   int sm_margin = 0;    // SMs the persistent SpMM kernel leaves free (for concurrently running NCCL kernels)
   int gemm_tc = 1;       // tcgen05 GEMMs where supported (0 = CUDA-core fp32 kernels only)
   int tc_launches = 0;
+  int tc_dbg_mode = 0;
   void* tc_dbg = nullptr;  // device buffer for per-CTA phase timestamps of the highway kernel (debug tool)   // read-only: tcgen05 kernels launched so far
   // profiling
   bool prof = false;

@@ -58,6 +58,7 @@ struct alignas(64) TcParams {
   float* T;
   int ldt;
   long long* dbg;  // optional per-CTA phase timestamps (tools/gemm_phases.py)
+  int dbg_mode;    // tools only: 1 = identity activations, 2 = no stores, 4 = no bias loads
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -364,7 +365,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float bh[4] = {0.f, 0.f, 0.f, 0.f}, bt[4] = {0.f, 0.f, 0.f, 0.f};
-            if (full_chunk) {
+            if (p.dbg_mode & 4) {
+            } else if (full_chunk) {
               const float4 u = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
               const float4 w = __ldg(reinterpret_cast<const float4*>(p.bias_t + col0) + j);
               bh[0] = u.x; bh[1] = u.y; bh[2] = u.z; bh[3] = u.w;
@@ -381,7 +383,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               h[e] = act_fn(acc[4 * j + e] + bh[e]);
-              t[e] = sigmoidf_(acc_t[4 * j + e] + bt[e]);
+              t[e] = (p.dbg_mode & 1) ? acc_t[4 * j + e] + bt[e] : sigmoidf_(acc_t[4 * j + e] + bt[e]);
               y[e] = t[e] * h[e] + (1.0f - t[e]) * xin[4 * j + e];
             }
             const uint32_t off = (j ^ swz) << 4;
@@ -390,7 +392,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             *reinterpret_cast<float4*>(ob + 2 * kBox + off) = make_float4(t[0], t[1], t[2], t[3]);
           }
         };
-        if (p.act == GCNB_ACT_TANH) body([](float z) { return tanhf_(z); });
+        if (p.dbg_mode & 1) body([](float z) { return z; });
+        else if (p.act == GCNB_ACT_TANH) body([](float z) { return tanhf_(z); });
         else if (p.act == GCNB_ACT_SIGMOID) body([](float z) { return sigmoidf_(z); });
         else if (p.act == GCNB_ACT_RELU) body([](float z) { return fmaxf(z, 0.f); });
         else body([](float z) { return z; });
@@ -399,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
       if (dbg && ct == 0) { e_ld += s1 - s0; e_math += s2 - s1; e_out += clock64() - s2; dbg[13] = e_ld; dbg[14] = e_math; dbg[15] = e_out; }
-      if (leader) {
+      if (leader && !(p.dbg_mode & 2)) {
         const uint32_t src = smem_u32(out_base);
         tma_store_2d(&p.mapOut[0], src, col0, m0);
         if (p.nphase == 2) {
@@ -771,6 +774,7 @@ int gcnb_highway_tc(gcnb_ctx* ctx, int n_rows, int hd, const float* S, int lds, 
   p.C = Y; p.ldc = ldy; p.bias = bh; p.act = act; p.accumulate = 0;
   p.bias_t = bt; p.X = X; p.ldx = ldx; p.H = H; p.ldh = ldh; p.T = T; p.ldt = ldt;
   p.dbg = reinterpret_cast<long long*>(ctx->tc_dbg);
+  p.dbg_mode = ctx->tc_dbg_mode;
   return launch(ctx, p);
 }
 

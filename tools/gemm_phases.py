@@ -45,6 +45,14 @@ e1.record(stream)
 torch.cuda.synchronize()
 print("highway kernel: %.3f ms per launch" % (e0.elapsed_time(e1) / 5))
 ctx.lib.gcnb_debug_set_tc_buffer(ctx.h, p(dbg))
+for mode in [1, 2, 3, 4, 7]:
+    ctx.set_option("tc_dbg_mode", mode)
+    run()
+    ctx.sync()
+    dd = dbg.cpu().numpy().reshape(-1, 16)
+    print("dbg_mode %d (1 = identity activations, 2 = no stores, 4 = no bias loads): epilogue median %.0f clk, math+staging %.0f"
+          % (mode, np.median(dd[:, 5] - dd[:, 4]), np.median(dd[:, 14])))
+ctx.set_option("tc_dbg_mode", 0)
 run()
 ctx.sync()
 d = dbg.cpu().numpy().reshape(-1, 16)
