@@ -183,3 +183,35 @@ def test_nonsymmetric_graph_uses_transpose(problem):
     r64 = gcn_ref.loss_and_grads(params, X, An, Y, tr, hid, True, None, 0.0, dtype="float64")
     for g, rg in zip(eng.get_grads(), r64["grads"]):
         np.testing.assert_allclose(g, rg, rtol=1e-3, atol=1e-4 * float(np.abs(rg).max()) + 1e-12)
+
+
+def test_uncached_inputs_reupload_gives_identical_results(problem):
+    """cache_device_inputs=False (bench.py's end-to-end leg): every call copies X, A_hat, X^T again on the copy
+    stream, overlapped with the forward pass; results must be bit-identical to the cached run, also when the host
+    arrays are modified in place between calls (same objects, new content)."""
+    A, X, Y, tr, dev, te, cfg = problem
+    hid = [300, 300]
+    outs = []
+    for cached in (True, False):
+        clf = _model(cfg, True, hid=hid)
+        clf.build_model(A, seed=11)
+        clf.cache_device_inputs = cached
+        o = [clf.f_train(X, Y[tr], Y[dev], A, tr, dev, seed=s, update=True) for s in (1, 2, 3)]
+        outs.append((o, clf.get_all_param_values(), clf.predict(X, A, te)[1]))
+    for a, b in zip(outs[0][0], outs[1][0]):
+        assert a == b
+    for a, b in zip(outs[0][1], outs[1][1]):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(outs[0][2], outs[1][2])
+    # in-place edit of the host matrices is picked up by the uncached model only
+    clf = _model(cfg, True, hid=hid, p=0.0)
+    clf.build_model(A, seed=11)
+    clf.cache_device_inputs = False
+    X2, A2 = X.copy(), A.copy()
+    l0 = clf.f_train(X2, Y[tr], Y[dev], A2, tr, dev, seed=1, update=False)[0]
+    X2.data *= np.float32(0.5)
+    l1 = clf.f_train(X2, Y[tr], Y[dev], A2, tr, dev, seed=1, update=False)[0]
+    params = [p.copy() for p in clf.init_params]
+    r = gcn_ref.loss_and_grads(params, X2, A2, Y, tr, hid, True, None, 0.0)
+    assert l0 != l1
+    np.testing.assert_allclose(l1, r["train_loss"], rtol=1e-3)
