@@ -83,6 +83,9 @@ SIGNATURES = {
     "gcnb_l1l2_f32": (C.c_int, [_ctxp, _vp, _vp, _i64, _f32, _vp]),
     "gcnb_adam_f32": (C.c_int, [_ctxp, _vp, _vp, _vp, _vp, _i64, _vp, _f32, _f32, _f32, _f32]),
     "gcnb_dropout_mask_u8": (C.c_int, [_ctxp, _i32, _i32, _f32, _u64, _i64, _vp]),
+    "gcnb_adj_workspace_bytes": (_sz, [_i64, _i32]),
+    "gcnb_adj_build_rows": (C.c_int, [_ctxp, _vp, _vp, _i64, _i32, _vp, _sz, _vp, C.POINTER(_i64)]),
+    "gcnb_adj_fill_f32": (C.c_int, [_ctxp, _i64, _i32, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

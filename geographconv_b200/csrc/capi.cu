@@ -98,6 +98,8 @@ static int* option_slot(gcnb_ctx* ctx, const char* name) {
   if (!strcmp(name, "spmm_unroll")) return &ctx->spmm_unroll;
   if (!strcmp(name, "gemm_tc")) return &ctx->gemm_tc;
   if (!strcmp(name, "sm_margin")) return &ctx->sm_margin;
+  if (!strcmp(name, "spmm_panel")) return &ctx->spmm_panel;
+  if (!strcmp(name, "spmm_panel_policy")) return &ctx->spmm_panel_policy;
   if (!strcmp(name, "tc_dbg_mode")) return &ctx->tc_dbg_mode;
   if (!strcmp(name, "tc_launches")) return &ctx->tc_launches;
   return nullptr;

@@ -18,6 +18,11 @@
 //      of shared-memory row slots armed with mbarriers; one lane issues a 1-D bulk copy per
 //      gathered row, the warp consumes rows from shared memory with conflict-free LDS.128.
 //      Persistent CTAs (one per SM) pull items from an atomic counter.
+//   2  L2-resident column panels: the product is computed one PW-column panel (PW = 16/32/64 floats) of B and
+//      C at a time, panel-major over the whole grid (blockIdx.y = panel).  A panel of B is rows x PW*4 bytes
+//      (N = 500k, PW = 32: 64 MB), so after its first touch every further gather of the panel is an L2 hit:
+//      B leaves HBM once per product instead of once per nonzero.  A warp is cut into 32/(PW/4) lane groups,
+//      each group owns one row item and walks its nonzeros in CSR order (same order-preserving sum).
 //
 // HBM model: per nonzero one K-wide fp32 row of B is read (K*4 B) plus 8 B of CSR;
 // per row K*4 B are written.
@@ -51,6 +56,9 @@ struct SpmmParams {
   const int* long_rows;
   int n_long;
   int* counter;
+  int pcol0;       // first column of this pass inside a partial slot (0 unless the slots span all of K: panel engine)
+  int k4;          // K rounded up to 4 (panel engine: the panels tile [0, k4))
+  int evict_last;  // panel engine: gathers carry an L2 evict_last hint
 };
 
 constexpr int kWarpsPerCta = 8;
@@ -169,7 +177,7 @@ __device__ __forceinline__ void spmm_store_item(const SpmmParams& p, const int4 
   if (it.w < 0) {
     spmm_epilogue<NCHUNK>(p, it.x, acc, lane);
   } else {
-    float4* dst = reinterpret_cast<float4*>(p.partial + (size_t)it.w * p.ldp);
+    float4* dst = reinterpret_cast<float4*>(p.partial + (size_t)it.w * p.ldp + p.pcol0);
 #pragma unroll
     for (int ch = 0; ch < NCHUNK; ++ch)
       if (lane + 32 * ch < p.nf4) dst[lane + 32 * ch] = acc[ch];
@@ -359,6 +367,131 @@ __global__ void __launch_bounds__(WARPS * 32, 1) spmm_bulk_kernel(const SpmmPara
 }
 
 // ---------------------------------------------------------------------------------------
+// variant 2: L2-resident column panels
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ld_gather_hint_f4(const float4* p, uint64_t pol) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p), "l"(pol));
+  return r;
+}
+
+// element-wise epilogue of one float4 of an output row (no row softmax: that needs the whole row, see
+// row_softmax_kernel).  Same arithmetic, in the same order, as spmm_epilogue.
+__device__ __forceinline__ void panel_epilogue(const SpmmParams& p, int row, int c, float4 acc) {
+  float v[4] = {acc.x, acc.y, acc.z, acc.w};
+  float4* cptr = reinterpret_cast<float4*>(p.C + (size_t)row * p.ldc + c);
+  if (p.accumulate == 2) {
+    const float4 o = *cptr;
+    v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
+  }
+  if (p.bias != nullptr) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+    v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+  }
+  if (p.act != GCNB_ACT_LINEAR) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = act_apply(p.act, v[e]);
+  }
+  if (p.thresh != 0u) {
+    const uint4 r = dropout_draw(p.seed, p.row0 + row, (uint32_t)(c >> 2));
+    v[0] = r.x < p.thresh ? v[0] * p.scale : 0.f;
+    v[1] = r.y < p.thresh ? v[1] * p.scale : 0.f;
+    v[2] = r.z < p.thresh ? v[2] * p.scale : 0.f;
+    v[3] = r.w < p.thresh ? v[3] * p.scale : 0.f;
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+    if (c + e >= p.K) v[e] = 0.f;  // padding columns stay zero
+  float4 o = make_float4(v[0], v[1], v[2], v[3]);
+  if (p.accumulate == 1) {
+    const float4 old = *cptr;
+    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+  }
+  st_stream_f4(cptr, o);
+}
+
+// GL lanes per row item (panel = 4*GL floats), R (column, value) pairs per lane and batch: GL*R gathers in flight
+template <int GL, int R>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_panel_kernel(const SpmmParams p) {
+  constexpr int G = 32 / GL;
+  constexpr int NB = GL * R;
+  const int lane = threadIdx.x & 31;
+  const int g = lane / GL, gl = lane % GL;
+  const int col0 = (int)blockIdx.y * (GL * 4);
+  const int item = (blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)) * G + g;
+  const bool valid = item < p.n_items;
+  int4 it = make_int4(0, 0, 0, -1);
+  if (valid) it = __ldg(p.items + item);
+  const int n = it.z - it.y;
+  const int nmax = __reduce_max_sync(0xffffffffu, n);
+  const bool lane_on = col0 + 4 * gl < p.k4;
+  const uint64_t pol = policy_evict_first();
+  const uint64_t keep = policy_evict_last();
+  const float4* Bs = reinterpret_cast<const float4*>(p.B + col0) + gl;
+  const size_t ldb4 = (size_t)(p.ldb >> 2);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int base = 0; base < nmax; base += NB) {
+    int c[R];
+    float a[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int k = base + r * GL + gl;
+      c[r] = 0;
+      a[r] = 0.f;
+      if (k < n) {
+        c[r] = ld_stream_s32(p.col + it.y + k, pol);
+        a[r] = ld_stream_f32(p.val + it.y + k, pol);
+      }
+    }
+    float4 x[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int cj = __shfl_sync(0xffffffffu, c[j / GL], j % GL, GL);
+      x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane_on && base + j < n) {
+        const float4* src = Bs + (size_t)cj * ldb4;
+        x[j] = p.evict_last ? ld_gather_hint_f4(src, keep) : ld_gather_f4(src);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const float aj = __shfl_sync(0xffffffffu, a[j / GL], j % GL, GL);
+      acc.x = fmaf(aj, x[j].x, acc.x);
+      acc.y = fmaf(aj, x[j].y, acc.y);
+      acc.z = fmaf(aj, x[j].z, acc.z);
+      acc.w = fmaf(aj, x[j].w, acc.w);
+    }
+  }
+  if (!valid || !lane_on) return;
+  if (it.w >= 0)
+    *reinterpret_cast<float4*>(p.partial + (size_t)it.w * p.ldp + col0 + 4 * gl) = acc;
+  else
+    panel_epilogue(p, it.x, col0 + 4 * gl, acc);
+}
+
+// row softmax in place over C (panel engine: the product and bias are already in C); optional copy of the logits
+template <int NCHUNK>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) row_softmax_kernel(const SpmmParams p, int n_rows) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  float4 acc[NCHUNK];
+  const float4* crow = reinterpret_cast<const float4*>(p.C + (size_t)row * p.ldc);
+#pragma unroll
+  for (int ch = 0; ch < NCHUNK; ++ch)
+    acc[ch] = lane + 32 * ch < p.nf4 ? crow[lane + 32 * ch] : make_float4(0.f, 0.f, 0.f, 0.f);
+  spmm_epilogue<NCHUNK>(p, row, acc, lane);
+}
+
+// ---------------------------------------------------------------------------------------
 // long rows: add the per-item partial sums in item order, then the epilogue
 // ---------------------------------------------------------------------------------------
 template <int NCHUNK>
@@ -371,7 +504,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_fixup_kernel(const Spm
 #pragma unroll
   for (int ch = 0; ch < NCHUNK; ++ch) acc[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int s = s0; s < s0 + ns; ++s) {
-    const float4* src = reinterpret_cast<const float4*>(p.partial + (size_t)s * p.ldp);
+    const float4* src = reinterpret_cast<const float4*>(p.partial + (size_t)s * p.ldp + p.pcol0);
 #pragma unroll
     for (int ch = 0; ch < NCHUNK; ++ch) {
       if (lane + 32 * ch < p.nf4) {
@@ -422,12 +555,82 @@ int launch_pass(gcnb_ctx* ctx, const SpmmParams& p, int engine, int unroll) {
 
 constexpr int kMaxPassCols = 512;
 
+template <int NCHUNK>
+void launch_fixup(gcnb_ctx* ctx, const SpmmParams& p) {
+  spmm_fixup_kernel<NCHUNK><<<cdiv(p.n_long, kWarpsPerCta), kWarpsPerCta * 32, 0, ctx->stream>>>(p);
+}
+template <int NCHUNK>
+void launch_softmax(gcnb_ctx* ctx, const SpmmParams& p, int n_rows) {
+  row_softmax_kernel<NCHUNK><<<cdiv(n_rows, kWarpsPerCta), kWarpsPerCta * 32, 0, ctx->stream>>>(p, n_rows);
+}
+
+// engine 2: every column panel of the product in one launch (panel-major), then the long-row fix-up and, when
+// asked for, the row softmax as a pass of its own
+int launch_panels(gcnb_ctx* ctx, const SpmmParams& p0, int n_rows, int K4, int unroll) {
+  int PW = ctx->spmm_panel;
+  if (PW != 16 && PW != 64) PW = 32;
+  SpmmParams p = p0;
+  p.softmax = 0;
+  p.logits = nullptr;
+  p.col0 = 0;
+  p.k4 = K4;
+  p.nf4 = K4 / 4;
+  p.ldp = K4;
+  p.evict_last = ctx->spmm_panel_policy == 1;
+  if (p.n_items > 0) {
+    const int GL = PW / 4, G = 32 / GL;
+    const dim3 grid(cdiv(p.n_items, kWarpsPerCta * G), cdiv(K4, PW));
+    const int threads = kWarpsPerCta * 32;
+    if (GL == 4) {
+      if (unroll >= 16) spmm_panel_kernel<4, 4><<<grid, threads, 0, ctx->stream>>>(p);
+      else spmm_panel_kernel<4, 2><<<grid, threads, 0, ctx->stream>>>(p);
+    } else if (GL == 8) {
+      if (unroll >= 16) spmm_panel_kernel<8, 2><<<grid, threads, 0, ctx->stream>>>(p);
+      else spmm_panel_kernel<8, 1><<<grid, threads, 0, ctx->stream>>>(p);
+    } else {
+      spmm_panel_kernel<16, 1><<<grid, threads, 0, ctx->stream>>>(p);
+    }
+    GCNB_LAUNCHED(ctx);
+  }
+  for (int pass = 0; pass < 2; ++pass) {  // 0: long-row fix-up, 1: row softmax
+    if (pass == 0 && p.n_long == 0) continue;
+    if (pass == 1 && !p0.softmax) continue;
+    SpmmParams q = p;
+    if (pass == 1) {
+      q.bias = nullptr; q.accumulate = 0; q.act = GCNB_ACT_LINEAR; q.thresh = 0u;
+      q.softmax = 1; q.logits = p0.logits;
+    }
+    for (int c0 = 0; c0 < K4; c0 += kMaxPassCols) {
+      const int w = (K4 - c0) < kMaxPassCols ? (K4 - c0) : kMaxPassCols;
+      q.col0 = c0; q.pcol0 = c0; q.nf4 = w / 4;
+      const int nchunk = (q.nf4 + 31) / 32;
+      if (pass == 0) {
+        switch (nchunk) {
+          case 1: launch_fixup<1>(ctx, q); break;
+          case 2: launch_fixup<2>(ctx, q); break;
+          case 3: launch_fixup<3>(ctx, q); break;
+          default: launch_fixup<4>(ctx, q); break;
+        }
+      } else {
+        switch (nchunk) {
+          case 1: launch_softmax<1>(ctx, q, n_rows); break;
+          case 2: launch_softmax<2>(ctx, q, n_rows); break;
+          case 3: launch_softmax<3>(ctx, q, n_rows); break;
+          default: launch_softmax<4>(ctx, q, n_rows); break;
+        }
+      }
+      GCNB_LAUNCHED(ctx);
+    }
+  }
+  return GCNB_OK;
+}
+
 }  // namespace
 
 extern "C" size_t gcnb_spmm_workspace_bytes(const gcnb_csr* A, int32_t K) {
   if (!A) return 0;
-  const int pass_cols = K < kMaxPassCols ? ((K + 3) / 4) * 4 : kMaxPassCols;
-  return 256 + (size_t)A->n_slots * pass_cols * sizeof(float);
+  // partial-sum slots of the long rows: one pass of columns (engines 0/1) or the whole row (panel engine)
+  return 256 + (size_t)A->n_slots * (((size_t)K + 3) / 4 * 4) * sizeof(float);
 }
 
 extern "C" int gcnb_csr_plan(const int32_t* rowptr, int32_t n_rows, int32_t chunk, int32_t* n_items,
@@ -526,6 +729,7 @@ extern "C" int gcnb_spmm_csr_f32(gcnb_ctx* ctx, const gcnb_csr* A, const float* 
     }
     p.seed = epi->seed; p.row0 = epi->row0; p.logits = epi->logits;
   }
+  if (engine == 2) return launch_panels(ctx, p, A->n_rows, K4, unroll);
   for (int c0 = 0; c0 < K4; c0 += kMaxPassCols) {
     const int w = (K4 - c0) < kMaxPassCols ? (K4 - c0) : kMaxPassCols;
     p.col0 = c0;

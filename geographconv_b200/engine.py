@@ -392,6 +392,12 @@ class Engine:
         self.AT_out = self.AT.retagged(capi.TAG_SPMM_A_NARROW) if self.AT is not None else None
         self.h2d_bytes_last_bind = hg.nbytes
 
+    def unbind(self):
+        """Drop the cache key of the bound (X, A): the next ``bind`` prepares and uploads them again."""
+        self.ctx.sync()
+        self.copy_ctx.sync()
+        self._bound_key = None
+
     def _upload_hot(self, hg, ctx=None):
         ctx = self.ctx if ctx is None else ctx
         ctx.call("gcnb_h2d", _ptr(self.X_hot), C.c_void_p(hg.X_hot.ctypes.data), hg.X_hot.nbytes)

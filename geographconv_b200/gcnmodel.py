@@ -131,6 +131,13 @@ class GraphConv():
             self._engine.set_params(self._host_params)
         return self._engine
 
+    def invalidate_inputs(self):
+        """Forget the prepared copies of X / A (pinned host staging + device CSR).  They are keyed on the identity,
+        shape and nnz of the SciPy objects, so a matrix edited IN PLACE between calls needs this; new objects are
+        picked up on their own."""
+        if self._engine is not None:
+            self._engine.unbind()
+
     # Lasagne get/set_all_param_values equivalents
     def get_all_param_values(self):
         if self._engine is None:

@@ -102,12 +102,16 @@ class CsrOnDevice:
 
 
 def spmm(A, B, bias=None, act="linear", softmax=False, dropout_p=0.0, seed=0, row0=0, accumulate_into=None,
-         want_logits=False, chunk=None, device=None, variant=None):
+         want_logits=False, chunk=None, device=None, variant=None, panel=None, unroll=None, accumulate_mode=None):
     """epilogue(A.B) for CSR ``A`` and dense ``B`` -- ``theano.sparse.structured_dot`` plus the
     fused bias / activation / dropout / softmax (gcnmodel.py:39-42,130-136,153-157)."""
     d = get_dev(device)
     if variant is not None:
         d.ctx.set_option("spmm_variant", variant)
+    if panel is not None:
+        d.ctx.set_option("spmm_panel", panel)
+    if unroll is not None:
+        d.ctx.set_option("spmm_unroll", unroll)
     B = np.asarray(B, dtype=np.float32)
     K = B.shape[1]
     csr = CsrOnDevice(d, A, chunk=chunk)
@@ -124,6 +128,8 @@ def spmm(A, B, bias=None, act="linear", softmax=False, dropout_p=0.0, seed=0, ro
     db = d.vec(bias) if bias is not None else None
     epi.bias = db.data_ptr() if db is not None else None
     epi.act, epi.softmax, epi.accumulate = ACT[act], int(bool(softmax)), int(accumulate_into is not None)
+    if accumulate_mode is not None:  # 2: C = epilogue(C + A.B), the pre-activation accumulate
+        epi.accumulate = int(accumulate_mode)
     epi.dropout_p, epi.seed, epi.row0 = float(dropout_p), int(seed), int(row0)
     epi.logits = dL.data_ptr() if dL is not None else None
     d.fence()
@@ -132,6 +138,10 @@ def spmm(A, B, bias=None, act="linear", softmax=False, dropout_p=0.0, seed=0, ro
     out = d.download(dC, rows, ldc, K)
     if variant is not None:
         d.ctx.set_option("spmm_variant", 0)
+    if panel is not None:
+        d.ctx.set_option("spmm_panel", 32)
+    if unroll is not None:
+        d.ctx.set_option("spmm_unroll", 0)
     if want_logits:
         return out, d.download(dL, rows, ldc, K)
     return out

@@ -216,6 +216,21 @@ int gcnb_adam_f32(gcnb_ctx* ctx, float* params, const float* grads, float* m, fl
 int gcnb_dropout_mask_u8(gcnb_ctx* ctx, int32_t n_rows, int32_t k, float p, uint64_t seed,
                          int64_t row0, uint8_t* mask);
 
+/* ---------------------------------------------------------------- A_hat construction -- */
+/* The normalised adjacency the reference builds on the host before the hot path (gcnmain.py:115-128):
+ *   adj = symmetric 0/1 adjacency of the undirected edge list (u[e], v[e]), duplicates merged;
+ *   setdiag(0); setdiag(1); d = 1/sqrt(row sums); A_hat = (D * adj) * D in float64, cast to float32.
+ * Output: CSR with ascending column indices inside each row (int32 / fp32, gcnmain.py:167-168).
+ * Two calls because the caller owns all memory: build_rows fills rowptr[n_nodes + 1] (device) and returns
+ * nnz to the host (one stream synchronisation); the caller allocates colidx / val of nnz entries and calls
+ * fill with the same workspace.  `u`, `v` are device int32 arrays; self loops and repeated / reversed edges
+ * are allowed (nx.Graph semantics); a node id outside [0, n_nodes) is GCNB_E_INVALID. */
+size_t gcnb_adj_workspace_bytes(int64_t n_edges, int32_t n_nodes);
+int gcnb_adj_build_rows(gcnb_ctx* ctx, const int32_t* u, const int32_t* v, int64_t n_edges, int32_t n_nodes,
+                        void* work, size_t work_bytes, int32_t* rowptr, int64_t* nnz_host);
+int gcnb_adj_fill_f32(gcnb_ctx* ctx, int64_t n_edges, int32_t n_nodes, const void* work, const int32_t* rowptr,
+                      int32_t* colidx, float* val);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,7 +34,7 @@ def _rand_csr(rng, n, m, avg, hub_rows=(), hub_deg=0, empty_every=0):
     return sp.csr_matrix((vals, cols.astype(np.int32), rowptr.astype(np.int32)), shape=(n, m))
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("K", [1, 4, 129, 256, 300, 512, 600])
 def test_spmm_plain(K, variant):
     from geographconv_b200 import layers
@@ -47,7 +47,7 @@ def test_spmm_plain(K, variant):
     assert not got[np.diff(A.indptr) == 0].any()
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_spmm_hub_rows_split_deterministically(variant):
     """A 100k-degree hub row (power-law graphs) is cut into items whose partial
     sums are added in item order: same answer on every run."""
@@ -126,6 +126,39 @@ def test_spmm_accumulate():
     C0 = rng.randn(200, 300).astype(np.float32)
     got = layers.spmm(A, B, accumulate_into=C0)
     _close(got, C0 + gcn_ref.structured_dot(A, B))
+
+
+@pytest.mark.parametrize("panel,unroll", [(16, 0), (16, 16), (32, 0), (32, 16), (64, 0)])
+def test_spmm_panel_engine_epilogues(panel, unroll):
+    """Engine 2 (L2-resident column panels): every epilogue the step uses, at each panel width; a row's sum is
+    accumulated in CSR order like the other engines, so the engines agree to the last bit on plain products."""
+    from geographconv_b200 import layers
+    rng = np.random.RandomState(panel + unroll)
+    A = _rand_csr(rng, 777, 640, 11, hub_rows=(5,), hub_deg=600, empty_every=9)
+    K = 300
+    B = (0.3 * rng.randn(640, K)).astype(np.float32)
+    b = rng.randn(K).astype(np.float32)
+    kw = dict(variant=2, panel=panel, unroll=unroll, chunk=256)
+    plain = layers.spmm(A, B, **kw)
+    np.testing.assert_array_equal(plain, layers.spmm(A, B, variant=0, chunk=256))
+    _close(plain, gcn_ref.structured_dot(A, B))
+    seed, row0, p = 0xABCDEF, 12345, 0.5
+    got = layers.spmm(A, B, bias=b, act="tanh", dropout_p=p, seed=seed, row0=row0, **kw)
+    keep = gcn_ref.dropout_keep_mask(seed, 777, K, p, row0=row0)
+    _close(got, np.tanh(gcn_ref.structured_dot(A, B) + b[None, :]) * keep / (1 - p), atol_scale=2e-5)
+    C0 = rng.randn(777, K).astype(np.float32)
+    _close(layers.spmm(A, B, accumulate_into=C0, **kw), C0 + gcn_ref.structured_dot(A, B))
+    got = layers.spmm(A, B, bias=b, act="tanh", accumulate_into=C0, accumulate_mode=2, **kw)
+    _close(got, np.tanh(C0 + gcn_ref.structured_dot(A, B) + b[None, :]), atol_scale=2e-5)
+    for Kc in (7, 129, 256):
+        Bc = rng.randn(640, Kc).astype(np.float32)
+        bc = rng.randn(Kc).astype(np.float32)
+        P, Z = layers.spmm(A, Bc, bias=bc, softmax=True, want_logits=True, **kw)
+        zw = gcn_ref.structured_dot(A, Bc) + bc[None, :]
+        _close(Z, zw)
+        _close(P, gcn_ref.softmax_rows(zw), atol_scale=1e-6)
+        P0 = layers.spmm(A, Bc, bias=bc, softmax=True, variant=0, chunk=256)
+        np.testing.assert_array_equal(P, P0)
 
 
 @pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])

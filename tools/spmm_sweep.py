@@ -52,7 +52,9 @@ def main():
     ap.add_argument("--alpha", type=float, default=None)
     ap.add_argument("--what", default="a")
     ap.add_argument("--chunks", default="256")
-    ap.add_argument("--variants", default="0:0,0:2,0:4,0:8,1:0")
+    ap.add_argument("--variants", default="0:0,0:2,0:4,0:8,1:0",
+                    help="comma list of engine:unroll[:panel[:policy]] (engine 2 = L2-resident column panels)")
+    ap.add_argument("--hot", action="store_true", help="X / X^T: drop the dense hot-column block first, like the engine")
     args = ap.parse_args()
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
@@ -63,6 +65,9 @@ def main():
         mats["A_hat.H"] = (synth.synthetic_graph(args.n, args.deg, 77, args.alpha), args.n)
     if "x" in args.what.split(",") or "xt" in args.what.split(","):
         X = synth.synthetic_features(args.n, args.f, args.xnnz, 77)
+        if args.hot:
+            from geographconv_b200.engine import split_hot_columns
+            X = split_hot_columns(X, 0.05, 1024)[2]
         if "x" in args.what.split(","):
             mats["X.W0"] = (X, args.f)
         if "xt" in args.what.split(","):
@@ -81,13 +86,17 @@ def main():
             csr.struct.engine, csr.struct.unroll = -1, 0
             m.ctx.sync()
             for v in args.variants.split(","):
-                var, unroll = [int(x) for x in v.split(":")]
+                f = [int(x) for x in v.split(":")] + [0, 0, 0]
+                var, unroll, panel, policy = f[0], f[1], f[2] or 32, f[3]
                 m.ctx.set_option("spmm_variant", var)
                 m.ctx.set_option("spmm_unroll", unroll)
+                m.ctx.set_option("spmm_panel", panel)
+                m.ctx.set_option("spmm_panel_policy", policy)
                 ms = time_spmm(m, csr, B, ld, Cbuf, ld, K)
                 gbs = csr.touched_bytes(K) / ms / 1e6
-                print("  chunk %5d variant %d unroll %d: %8.3f ms  %7.1f GB/s  %.3f of HBM peak  (items %d, long rows %d)"
-                      % (chunk, var, unroll, ms, gbs, gbs / peak, csr.n_items, csr.n_long), flush=True)
+                extra = " panel %d policy %d" % (panel, policy) if var == 2 else ""
+                print("  chunk %5d variant %d unroll %d%s: %8.3f ms  %7.1f GB/s  %.3f of HBM peak  (items %d, long rows %d)"
+                      % (chunk, var, unroll, extra, ms, gbs, gbs / peak, csr.n_items, csr.n_long), flush=True)
 
 
 if __name__ == "__main__":
