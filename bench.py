@@ -261,9 +261,10 @@ def run_gpu(args, cfg, wname):
     roof = None
     traffic = args.ncu_traffic_bytes
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    kname = ["spmm_ldg_kernel", "spmm_bulk_kernel", "spmm_panel_kernel"][eng.A.engine_for(eng, eng.ldh[0], hd)]
     if traffic is None and world == 1 and os.path.exists(tpath):
         tj = json.load(open(tpath))
-        if tj.get("workload") == wname and args.alpha is None:
+        if tj.get("workload") == wname and args.alpha is None and tj.get("kernel", "").startswith(kname):
             traffic = tj["dram_bytes_per_launch"]  # from the committed ncu --set full capture of this kernel
     if spmm_ops:
         t_launch = spmm_ms / (spmm_ops / pieces) * 1e-3  # all pieces of one product
@@ -274,10 +275,13 @@ def run_gpu(args, cfg, wname):
         ach = float(tms2.item())
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic,
-                "kernel": "%s (A_hat.H, K=%d)" % ("spmm_bulk_kernel" if (hd > 256 and N / world * 1280 > (96 << 20)) else "spmm_ldg_kernel", hd),
+                "kernel": "%s (A_hat.H, K=%d)" % (kname, hd),
                 "algorithmic_bytes_per_launch": b_touch, "launches_timed": spmm_ops, "launches_per_product": pieces,
                 "avg_launch_ms": spmm_ms / spmm_ops * pieces, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
                 "per_rank": world > 1}
+        if kname == "spmm_panel_kernel":
+            roof["note"] = ("L2-resident column panels: B leaves HBM once per product, the per-nonzero gathers are L2 hits, so "
+                            "algorithmic B_touch / t may exceed the HBM peak; `traffic` is the DRAM bytes ncu counted")
     split = {k: round(v[0] / args.steps, 4) for k, v in prof.items()}
 
     # ---- end-to-end leg through GraphConv.f_train with host buffers ----

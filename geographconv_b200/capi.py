@@ -65,6 +65,7 @@ SIGNATURES = {
     "gcnb_copy2d_f32": (C.c_int, [_ctxp, _vp, _i32, _vp, _i32, _i32, _i32]),
     "gcnb_csr_plan": (C.c_int, [_vp, _i32, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), _vp, _vp]),
     "gcnb_spmm_csr_f32": (C.c_int, [_ctxp, C.POINTER(GcnbCsr), _vp, _i32, _vp, _i32, _i32, C.POINTER(GcnbEpilogue)]),
+    "gcnb_spmm_engine_for": (C.c_int, [_ctxp, C.POINTER(GcnbCsr), _i32, _i32]),
     "gcnb_spmm_workspace_bytes": (_sz, [C.POINTER(GcnbCsr), _i32]),
     "gcnb_gemm_f32": (C.c_int, [_ctxp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _i32]),
     "gcnb_gemm_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),

@@ -555,6 +555,26 @@ int launch_pass(gcnb_ctx* ctx, const SpmmParams& p, int engine, int unroll) {
 
 constexpr int kMaxPassCols = 512;
 
+// Gather engine of one product.  A->engine >= 0 names it, -1 defers to the context option, -2 chooses from the
+// shapes (measured on B200, C3 shapes, profiles/r1c_spmm_panel_sweep.txt and r1_spmm_sweep.txt):
+//  * the dense operand is larger than L2 can trivially hold (> 32 MB) but one 32-column panel of it
+//    (n_cols x 128 B) fits (<= 80 MB): L2-resident column panels -- A_hat.H at K=300 2.30 ms vs 3.37 ms for the
+//    best HBM gather, K=256 1.70 vs 2.34 ms, X_cold.W0 5.74 vs 7.51 ms;
+//  * else, operand > 96 MB and rows wider than 64 float4 lanes: bulk-copy staged gather (91% of the HBM copy rate
+//    vs 71-78% for register gathers);
+//  * else (L2-resident operands, narrow rows): LDG register gather, 2 nonzeros per batch.
+void pick_engine(const gcnb_ctx* ctx, const gcnb_csr* A, int ldb, int K4, int* engine, int* unroll) {
+  *engine = A->engine >= 0 ? A->engine : ctx->spmm_variant;
+  *unroll = A->unroll > 0 ? A->unroll : ctx->spmm_unroll;
+  if (A->engine == -2) {
+    const size_t operand_bytes = (size_t)A->n_cols * (size_t)ldb * sizeof(float);
+    const size_t panel_bytes = (size_t)A->n_cols * 128;
+    if (operand_bytes > ((size_t)32 << 20) && panel_bytes <= ((size_t)80 << 20) && K4 >= 64) *engine = 2;
+    else *engine = (operand_bytes > ((size_t)96 << 20) && K4 > 256) ? 1 : 0;
+    if (*unroll == 0 && *engine != 2) *unroll = 2;
+  }
+}
+
 template <int NCHUNK>
 void launch_fixup(gcnb_ctx* ctx, const SpmmParams& p) {
   spmm_fixup_kernel<NCHUNK><<<cdiv(p.n_long, kWarpsPerCta), kWarpsPerCta * 32, 0, ctx->stream>>>(p);
@@ -566,9 +586,10 @@ void launch_softmax(gcnb_ctx* ctx, const SpmmParams& p, int n_rows) {
 
 // engine 2: every column panel of the product in one launch (panel-major), then the long-row fix-up and, when
 // asked for, the row softmax as a pass of its own
-int launch_panels(gcnb_ctx* ctx, const SpmmParams& p0, int n_rows, int K4, int unroll) {
+int launch_panels(gcnb_ctx* ctx, const SpmmParams& p0, int n_rows, int K4, int unroll, bool A_engine_auto) {
   int PW = ctx->spmm_panel;
   if (PW != 16 && PW != 64) PW = 32;
+  if (A_engine_auto) PW = 32;
   SpmmParams p = p0;
   p.softmax = 0;
   p.logits = nullptr;
@@ -576,7 +597,7 @@ int launch_panels(gcnb_ctx* ctx, const SpmmParams& p0, int n_rows, int K4, int u
   p.k4 = K4;
   p.nf4 = K4 / 4;
   p.ldp = K4;
-  p.evict_last = ctx->spmm_panel_policy == 1;
+  p.evict_last = ctx->spmm_panel_policy != 0;
   if (p.n_items > 0) {
     const int GL = PW / 4, G = 32 / GL;
     const dim3 grid(cdiv(p.n_items, kWarpsPerCta * G), cdiv(K4, PW));
@@ -631,6 +652,13 @@ extern "C" size_t gcnb_spmm_workspace_bytes(const gcnb_csr* A, int32_t K) {
   if (!A) return 0;
   // partial-sum slots of the long rows: one pass of columns (engines 0/1) or the whole row (panel engine)
   return 256 + (size_t)A->n_slots * (((size_t)K + 3) / 4 * 4) * sizeof(float);
+}
+
+extern "C" int gcnb_spmm_engine_for(const gcnb_ctx* ctx, const gcnb_csr* A, int32_t ldb, int32_t K) {
+  if (!ctx || !A) return GCNB_E_INVALID;
+  int engine = 0, unroll = 0;
+  pick_engine(ctx, A, ldb, ((K + 3) / 4) * 4, &engine, &unroll);
+  return engine;
 }
 
 extern "C" int gcnb_csr_plan(const int32_t* rowptr, int32_t n_rows, int32_t chunk, int32_t* n_items,
@@ -693,16 +721,8 @@ extern "C" int gcnb_spmm_csr_f32(gcnb_ctx* ctx, const gcnb_csr* A, const float* 
   }
   if (A->n_rows == 0) return GCNB_OK;
   const size_t need = gcnb_spmm_workspace_bytes(A, K);
-  int engine = A->engine >= 0 ? A->engine : ctx->spmm_variant;
-  int unroll = A->unroll > 0 ? A->unroll : ctx->spmm_unroll;
-  if (A->engine == -2) {
-    // auto (measured on B200, profiles/r1_spmm_sweep.txt): when the gathered operand cannot live in L2 and a row
-    // spans more than 64 float4 lanes (K > 256) the bulk-copy staged engine reaches 91% of the HBM copy rate vs
-    // 71-78% for register gathers; L2-resident operands and narrower rows are fastest with LDG, 2 nonzeros/batch
-    const size_t operand_bytes = (size_t)A->n_cols * (size_t)ldb * sizeof(float);
-    engine = (operand_bytes > ((size_t)96 << 20) && K4 > 256) ? 1 : 0;
-    if (unroll == 0) unroll = 2;
-  }
+  int engine, unroll;
+  pick_engine(ctx, A, ldb, K4, &engine, &unroll);
   if (A->n_slots > 0 || engine == 1) {
     if (!ctx->ws || ctx->ws_bytes < need)
       return gcnb_fail(ctx, GCNB_E_WORKSPACE, "spmm needs %s%lld workspace bytes, have %lld", "", (long long)need,
@@ -729,7 +749,7 @@ extern "C" int gcnb_spmm_csr_f32(gcnb_ctx* ctx, const gcnb_csr* A, const float* 
     }
     p.seed = epi->seed; p.row0 = epi->row0; p.logits = epi->logits;
   }
-  if (engine == 2) return launch_panels(ctx, p, A->n_rows, K4, unroll);
+  if (engine == 2) return launch_panels(ctx, p, A->n_rows, K4, unroll, A->engine == -2);
   for (int c0 = 0; c0 < K4; c0 += kMaxPassCols) {
     const int w = (K4 - c0) < kMaxPassCols ? (K4 - c0) : kMaxPassCols;
     p.col0 = c0;

@@ -71,6 +71,13 @@ class HostCsr:
         self.nnz = int(M.nnz)
         rowptr = np.ascontiguousarray(M.indptr, dtype=np.int32)
         items, long_rows, n_slots = capi.csr_plan(rowptr, int(chunk))
+        # Skewed row lengths (X^T's rows are term frequencies, power-law graphs have hubs): longest items first.
+        # The panel engine walks four to eight items per warp in lock step and the persistent engine pulls items
+        # from a counter, so neighbours of equal length and a short tail both pay.  Results do not depend on the
+        # order (every item owns its output row or its partial-sum slot).
+        lens = items[:, 2] - items[:, 1] if len(items) else np.zeros(0, dtype=np.int32)
+        if len(lens) and int(lens.max()) > 4 * max(float(lens.mean()), 1.0):
+            items = np.ascontiguousarray(items[np.argsort(-lens, kind="stable")])
         self.rowptr = _pinned(rowptr)
         self.colidx = _pinned(np.ascontiguousarray(M.indices, dtype=np.int32))
         self.val = _pinned(np.ascontiguousarray(M.data, dtype=np.float32))
@@ -202,6 +209,10 @@ class DeviceCsr:
         s.tag = int(tag)
         other.struct = s
         return other
+
+    def engine_for(self, eng, ldb, K):
+        """Gather engine (0 LDG, 1 bulk copy, 2 L2-resident panels) gcnb_spmm_csr_f32 uses for this product."""
+        return int(eng.lib.gcnb_spmm_engine_for(eng.ctx.h, C.byref(self.struct), int(ldb), int(K)))
 
     def touched_bytes(self, K):
         """SURVEY.md 8d B_touch: nnz*(4+4) + (rows+1)*4 + nnz*K*4 + rows*K*4."""

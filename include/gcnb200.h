@@ -67,7 +67,9 @@ const char* gcnb_last_error(const gcnb_ctx* ctx);
 int gcnb_set_stream(gcnb_ctx* ctx, void* stream);
 void* gcnb_get_stream(const gcnb_ctx* ctx);
 int gcnb_set_workspace(gcnb_ctx* ctx, void* dev_ptr, size_t bytes);
-/* named integer options: "spmm_variant" (0 = LDG.128 register gather, 1 = bulk-copy/TMA staged),
+/* named integer options: "spmm_variant" (0 = LDG.128 register gather, 1 = bulk-copy/TMA staged, 2 = L2-resident
+ * column panels), "spmm_panel" (panel width of engine 2 in floats: 16, 32, 64), "spmm_panel_policy" (1 = panel
+ * gathers carry an L2 evict_last hint),
  * "spmm_unroll" (nonzeros gathered per batch), "gemm_tc" (1 = tcgen05 path where supported, the
  * default), "tc_launches" (read-only count of tcgen05 kernels launched), "sm_margin" (SMs the persistent
  * SpMM kernel leaves to concurrently running collectives). */
@@ -110,10 +112,11 @@ typedef struct gcnb_csr {
   int32_t n_long;
   int32_t n_slots;
   int32_t tag; /* gcnb_tag the SpMM time is booked under */
-  /* gather engine for this matrix: 0 = LDG.128 register gather (best when the dense operand is L2
-   * resident, e.g. X.W0), 1 = bulk-copy (TMA engine) staged gather with persistent CTAs (best when
-   * the gathered rows come from HBM, e.g. A_hat.H), -1 = the context's "spmm_variant" option,
-   * -2 = choose per call from the operand size and K */
+  /* gather engine for this matrix: 0 = LDG.128 register gather (best when the whole dense operand is L2
+   * resident), 1 = bulk-copy (TMA engine) staged gather with persistent CTAs (best when the gathered rows
+   * must come from HBM), 2 = L2-resident column panels (the product is computed 32 columns of B at a time,
+   * panel-major, so B leaves HBM once per product; best when one n_cols x 128 B panel fits L2, e.g. A_hat.H
+   * at N = 500k), -1 = the context's "spmm_variant" option, -2 = choose per call from the operand size and K */
   int32_t engine;
   int32_t unroll; /* nonzeros gathered per batch by engine 0 (2, 4, 8); 0 = the context's / auto */
 } gcnb_csr;
@@ -142,6 +145,8 @@ typedef struct gcnb_epilogue {
  * its gradient structured_dot(a.T, g).  `epi` may be NULL (plain product). */
 int gcnb_spmm_csr_f32(gcnb_ctx* ctx, const gcnb_csr* A, const float* B, int32_t ldb, float* C,
                       int32_t ldc, int32_t K, const gcnb_epilogue* epi);
+/* the gather engine (0, 1, 2) the call above would use for this matrix, leading dimension of B and K */
+int gcnb_spmm_engine_for(const gcnb_ctx* ctx, const gcnb_csr* A, int32_t ldb, int32_t K);
 /* workspace bytes the call above needs for this matrix and K */
 size_t gcnb_spmm_workspace_bytes(const gcnb_csr* A, int32_t K);
 
