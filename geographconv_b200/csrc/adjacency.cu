@@ -11,9 +11,10 @@
 //   2. scan       exclusive prefix sum -> bucket offsets
 //   3. scatter    every edge end drops its neighbour id into the bucket of its node (atomic cursor; the order
 //                 inside a bucket is arbitrary and is erased by the next step)
-//   4. sort       each bucket is sorted in place: a warp per bucket in shared memory (<= 128 entries), a CTA per
-//                 bucket in shared memory (<= 4096) or in place in global memory (hubs of power-law graphs),
-//                 all with the same all-ascending ("flip") bitonic network; distinct entries are counted
+//   4. sort       each bucket is sorted in place: a warp per bucket in shared memory (<= 128 entries) or a CTA per
+//                 bucket in shared memory (<= 4096) with an all-ascending ("flip") bitonic network; hubs of
+//                 power-law graphs (> 4096 entries) go through an n-bit presence bitmap instead (set, then
+//                 enumerate in order: O(n/32 + m) instead of O(m log^2 m)); distinct entries are counted
 //   5. scan       distinct counts -> rowptr of A_hat
 //   6. fill       distinct neighbours are compacted into colidx (ascending inside a row) and
 //                 val = float32( (d_i * 1.0) * d_j ) with d = 1/sqrt(double(row nnz)): the float64 arithmetic and
@@ -29,8 +30,9 @@ constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;
 constexpr int kWarpRowMax = 128;  // bucket sizes a single warp sorts in shared memory
-constexpr int kCtaRowMax = 4096;  // bucket sizes a CTA sorts in shared memory; larger buckets are sorted in global memory
+constexpr int kCtaRowMax = 4096;  // bucket sizes a CTA sorts in shared memory; larger buckets use the bitmap path
 constexpr int kSortThreads = 512;
+constexpr int kBigCtas = 128;     // CTAs of the big-bucket kernel (each owns one n-bit bitmap in the workspace)
 
 struct AdjWork {  // carved out of the caller's workspace (all 256-byte aligned)
   int* cnt;       // n+1: raw bucket sizes, later reused for the distinct counts
@@ -40,6 +42,7 @@ struct AdjWork {  // carved out of the caller's workspace (all 256-byte aligned)
   int* tmp;       // scan block sums
   int* flags;     // [0] out-of-range edge seen, [1] number of big buckets
   double* dinv;   // n
+  unsigned* bitmaps;  // kBigCtas x ceil(n / 32)
   int* raw;       // 2E + n
 };
 
@@ -61,8 +64,9 @@ __host__ size_t carve(AdjWork* w, char* base, long long n_edges, int n) {
   int* tmp = (int*)take(nblocks * 4);
   int* flags = (int*)take(256);
   double* dinv = (double*)take(n1 * 8);
+  unsigned* bitmaps = (unsigned*)take((size_t)kBigCtas * ((n1 + 31) / 32) * 4);
   int* raw = (int*)take(((size_t)2 * (size_t)n_edges + n1) * 4);
-  if (w) *w = AdjWork{cnt, rawptr, cursor, biglist, tmp, flags, dinv, raw};
+  if (w) *w = AdjWork{cnt, rawptr, cursor, biglist, tmp, flags, dinv, bitmaps, raw};
   return off;
 }
 
@@ -276,25 +280,67 @@ __global__ void __launch_bounds__(256) adj_sort_small(const int* __restrict__ ra
 }
 
 __global__ void __launch_bounds__(kSortThreads) adj_sort_big(const int* __restrict__ rawptr, int* raw, int* distinct,
-                                                             const int* __restrict__ biglist, const int* flags) {
+                                                             const int* __restrict__ biglist, const int* flags, int n,
+                                                             unsigned* bitmaps) {
   __shared__ int buf[kCtaRowMax];
+  __shared__ int wtot[kSortThreads / 32];
   const int nbig = flags[1];
+  const int words = (n + 31) >> 5;
+  unsigned* bm = bitmaps + (size_t)blockIdx.x * (size_t)(((size_t)n + 1 + 31) / 32);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int q = blockIdx.x; q < nbig; q += gridDim.x) {
     const int r = biglist[q];
     const int b = rawptr[r], m = rawptr[r + 1] - b;
     int* a = raw + b;
     if (m <= kCtaRowMax) {
-      for (int i = threadIdx.x; i < m; i += kSortThreads) buf[i] = a[i];
+      for (int i = tid; i < m; i += kSortThreads) buf[i] = a[i];
       __syncthreads();
-      bitonic_flip_sort(buf, m, threadIdx.x, kSortThreads, [] { __syncthreads(); });
-      for (int i = threadIdx.x; i < m; i += kSortThreads) a[i] = buf[i];
+      bitonic_flip_sort(buf, m, tid, kSortThreads, [] { __syncthreads(); });
+      for (int i = tid; i < m; i += kSortThreads) a[i] = buf[i];
+      __syncthreads();
+      if (tid < 32) {
+        const int d = warp_count_distinct(a, m, tid);
+        if (tid == 0) distinct[r] = d;
+      }
     } else {
-      bitonic_flip_sort(a, m, threadIdx.x, kSortThreads, [] { __syncthreads(); });
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      const int d = warp_count_distinct(a, m, threadIdx.x);
-      if (threadIdx.x == 0) distinct[r] = d;
+      // presence bitmap over the node ids, then the set bits in ascending order are the sorted distinct neighbours;
+      // the tail of the bucket repeats the largest one so that the bucket stays "sorted with duplicates"
+      for (int i = tid; i < words; i += kSortThreads) bm[i] = 0u;
+      __syncthreads();
+      for (int i = tid; i < m; i += kSortThreads) {
+        const int x = a[i];
+        atomicOr(bm + (x >> 5), 1u << (x & 31));
+      }
+      __syncthreads();
+      const int per = (words + kSortThreads - 1) / kSortThreads;
+      const int w0 = min(tid * per, words), w1 = min(w0 + per, words);
+      int c = 0;
+      for (int w = w0; w < w1; ++w) c += __popc(bm[w]);
+      int x = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      if (lane == 31) wtot[warp] = x;
+      __syncthreads();
+      int off = x - c, d = 0;
+      for (int w = 0; w < kSortThreads / 32; ++w) {
+        if (w < warp) off += wtot[w];
+        d += wtot[w];
+      }
+      for (int w = w0; w < w1; ++w) {
+        unsigned bits = bm[w];
+        while (bits) {
+          const int t = __ffs(bits) - 1;
+          bits &= bits - 1;
+          a[off++] = (w << 5) | t;
+        }
+      }
+      __syncthreads();
+      const int last = a[d - 1];
+      for (int i = d + tid; i < m; i += kSortThreads) a[i] = last;
+      if (tid == 0) distinct[r] = d;
     }
     __syncthreads();
   }
@@ -381,7 +427,7 @@ extern "C" int gcnb_adj_build_rows(gcnb_ctx* ctx, const int32_t* u, const int32_
     // distinct counts overwrite the raw counts (the bucket offsets are already in rawptr)
     adj_sort_small<<<cdiv(n, 8), 256, 0, ctx->stream>>>(w.rawptr, w.raw, n, w.cnt, w.biglist, w.flags);
     GCNB_LAUNCHED(ctx);
-    adj_sort_big<<<ctx->sm_count * 2, kSortThreads, 0, ctx->stream>>>(w.rawptr, w.raw, w.cnt, w.biglist, w.flags);
+    adj_sort_big<<<kBigCtas, kSortThreads, 0, ctx->stream>>>(w.rawptr, w.raw, w.cnt, w.biglist, w.flags, n, w.bitmaps);
     GCNB_LAUNCHED(ctx);
   }
   rc = exclusive_scan(ctx, w.cnt, rowptr, n + 1, w.tmp);

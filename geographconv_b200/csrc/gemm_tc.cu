@@ -159,6 +159,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   const uint32_t stage_bytes = 2 * half_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * stage_bytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 2);
+  // [2][kMaxBN] bias (bh) and gate bias (bt) of this tile; 16-byte aligned (barriers end at +88, the slot at +92)
+  float* bias_s = reinterpret_cast<float*>(tmem_slot + 6);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_full = smem_u32(bars), bar_conv = bar_full + 8 * kStages, bar_empty = bar_conv + 8 * kStages;
   const uint32_t bar_acc = bar_empty + 8 * kStages, bar_in = bar_acc + 8;
@@ -181,6 +183,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                  "n"(kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x >= 64 && (int)threadIdx.x - 64 < kMaxBN) {
+    // the tile's bias slices, read once per CTA: the epilogue takes them from shared memory (broadcast reads) instead
+    // of 16 dependent global loads per thread and chunk (4.8k of the 22k epilogue clocks, tools/gemm_phases.py)
+    const int c = (int)threadIdx.x - 64, col = n0 + c;
+    const bool on = c < BN && col < p.N && !(p.dbg_mode & 4);
+    const bool use_bias = p.nphase == 2 || (!p.accumulate && p.bias != nullptr);
+    bias_s[c] = (on && use_bias) ? __ldg(p.bias + col) : 0.f;
+    bias_s[kMaxBN + c] = (on && p.nphase == 2) ? __ldg(p.bias_t + col) : 0.f;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -330,23 +341,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       }
       first = false;
       unsigned char* ob = out_base + (size_t)r * 128;
-      const bool full_chunk = col0 + 32 <= p.N;  // bias vectors are only guaranteed up to N rounded to 4
+      const float4* bs = reinterpret_cast<const float4*>(bias_s + ch * 32);
       if (p.nphase == 1) {
-        const bool use_bias = !p.accumulate && p.bias != nullptr;
         auto body = [&](auto act_fn) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float b[4] = {0.f, 0.f, 0.f, 0.f};
-            if (use_bias) {
-              if (full_chunk) {
-                const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
-                b[0] = bv.x; b[1] = bv.y; b[2] = bv.z; b[3] = bv.w;
-              } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  if (col0 + 4 * j + e < p.N) b[e] = __ldg(p.bias + col0 + 4 * j + e);
-              }
-            }
+            const float4 bv = bs[j];
+            const float b[4] = {bv.x, bv.y, bv.z, bv.w};
             float o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e)
@@ -361,24 +362,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       } else {
         float acc_t[32];
         tmem_ld32(tlane + (uint32_t)(BN + ch * 32), acc_t);
+        const float4* bts = reinterpret_cast<const float4*>(bias_s + kMaxBN + ch * 32);
         auto body = [&](auto act_fn) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float bh[4] = {0.f, 0.f, 0.f, 0.f}, bt[4] = {0.f, 0.f, 0.f, 0.f};
-            if (p.dbg_mode & 4) {
-            } else if (full_chunk) {
-              const float4 u = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
-              const float4 w = __ldg(reinterpret_cast<const float4*>(p.bias_t + col0) + j);
-              bh[0] = u.x; bh[1] = u.y; bh[2] = u.z; bh[3] = u.w;
-              bt[0] = w.x; bt[1] = w.y; bt[2] = w.z; bt[3] = w.w;
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (col0 + 4 * j + e < p.N) {
-                  bh[e] = __ldg(p.bias + col0 + 4 * j + e);
-                  bt[e] = __ldg(p.bias_t + col0 + 4 * j + e);
-                }
-            }
+            const float4 u = bs[j], w = bts[j];
+            const float bh[4] = {u.x, u.y, u.z, u.w}, bt[4] = {w.x, w.y, w.z, w.w};
             float h[4], t[4], y[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -664,7 +653,9 @@ void pick_bn(int N, int* bn, int* n_tiles) {
   *n_tiles = (N + *bn - 1) / *bn;
 }
 
-size_t smem_bytes(int BN) { return (size_t)kStages * 2 * (BM * 128 + BN * 128) + (3 * kStages + 2) * 8 + 16 + 1024; }
+size_t smem_bytes(int BN) {
+  return (size_t)kStages * 2 * (BM * 128 + BN * 128) + (3 * kStages + 2) * 8 + 32 + 2 * kMaxBN * sizeof(float) + 1024;
+}
 
 int launch(gcnb_ctx* ctx, const TcParams& p) {
   const size_t smem = smem_bytes(p.BN);

@@ -57,10 +57,65 @@ def _pinned(arr):
         return arr
 
 
+def panel_col_blocks(n_cols, target_bytes=16 << 20, max_blocks=8):
+    """Column ranges to cut the rows of a panel-engine operand into so that the live part of one 32-column panel of
+    the dense operand (n_cols / blocks rows x 128 B) is about ``target_bytes``.  Measured on C3's X^T.dz (64 MB
+    panel): 1 block 9.4 ms, 2 blocks 6.5 ms, 4 blocks 5.3 ms, 8 blocks 5.5 ms (profiles/r1c_spmm_panel_sweep.txt)."""
+    return int(min(max_blocks, max(1, -(-int(n_cols) * 128 // int(target_bytes)))))
+
+
+def plan_col_blocks(rowptr, colidx, n_cols, n_blocks, chunk):
+    """Row-item plan whose items never straddle a boundary between ``n_blocks`` equal ranges of column ids.
+
+    The panel engine keeps one 32-column panel of the dense operand in L2; cutting every row at the column-range
+    boundaries and running the items range by range (all items of range 0, then range 1, ...) shrinks the live part
+    of the panel to n_cols/n_blocks rows: a 64 MB panel (N = 500k) becomes two 32 MB halves that the L2 of either
+    die holds.  Same item / long-row format as gcnb_csr_plan (a row with more than one item is a long row whose
+    items write partial sums that the fix-up adds in slot order = column order), so results stay deterministic.
+    Returns (items[n,4], long_rows[m,3], n_slots)."""
+    rowptr = np.asarray(rowptr, dtype=np.int64)
+    n_rows = len(rowptr) - 1
+    deg = np.diff(rowptr)
+    rows_of = np.repeat(np.arange(n_rows, dtype=np.int64), deg)
+    key = rows_of * n_cols + np.asarray(colidx, dtype=np.int64)
+    base = np.arange(n_rows, dtype=np.int64) * n_cols
+    cuts = [rowptr[:-1]]
+    for b in range(1, n_blocks):
+        cuts.append(np.searchsorted(key, base + (n_cols * b + n_blocks - 1) // n_blocks))
+    cuts.append(rowptr[1:])
+    seg_len = [cuts[b + 1] - cuts[b] for b in range(n_blocks)]
+    pieces = [(l + chunk - 1) // chunk for l in seg_len]
+    pieces[0] = np.where(deg == 0, 1, pieces[0])  # an empty row still owns one (empty) item: its epilogue must run
+    total = np.sum(pieces, axis=0)
+    is_long = total > 1
+    slot_base = np.zeros(n_rows, dtype=np.int64)
+    slot_base[is_long] = np.cumsum(total[is_long]) - total[is_long]
+    n_slots = int(total[is_long].sum())
+    long_ids = np.nonzero(is_long)[0]
+    long_rows = np.stack([long_ids, slot_base[long_ids], total[long_ids]], axis=1).astype(np.int32) if len(long_ids) \
+        else np.zeros((0, 3), dtype=np.int32)
+    out = []
+    before = np.zeros(n_rows, dtype=np.int64)  # pieces of the row in earlier blocks
+    for b in range(n_blocks):
+        pb = pieces[b]
+        r = np.repeat(np.arange(n_rows, dtype=np.int64), pb)
+        q = np.arange(len(r), dtype=np.int64) - np.repeat(np.cumsum(pb) - pb, pb)
+        per = (seg_len[b][r] + np.maximum(pb[r], 1) - 1) // np.maximum(pb[r], 1)
+        beg = cuts[b][r] + q * per
+        end = np.minimum(beg + per, cuts[b + 1][r])
+        slot = np.where(is_long[r], slot_base[r] + before[r] + q, -1)
+        it = np.stack([r, beg, end, slot], axis=1)
+        it = it[np.argsort(-(end - beg), kind="stable")]  # longest first inside a block
+        out.append(it)
+        before += pb
+    items = np.ascontiguousarray(np.concatenate(out, axis=0).astype(np.int32)) if out else np.zeros((0, 4), np.int32)
+    return items, long_rows, n_slots
+
+
 class HostCsr:
     """Host-side CSR of one SpMM operand: int32 / fp32 arrays in pinned memory plus the row-item plan."""
 
-    def __init__(self, M, chunk):
+    def __init__(self, M, chunk, col_blocks=1):
         M = M.tocsr()
         if not M.has_sorted_indices:
             M = M.copy()
@@ -70,14 +125,18 @@ class HostCsr:
         self.shape = tuple(int(x) for x in M.shape)
         self.nnz = int(M.nnz)
         rowptr = np.ascontiguousarray(M.indptr, dtype=np.int32)
-        items, long_rows, n_slots = capi.csr_plan(rowptr, int(chunk))
-        # Skewed row lengths (X^T's rows are term frequencies, power-law graphs have hubs): longest items first.
-        # The panel engine walks four to eight items per warp in lock step and the persistent engine pulls items
-        # from a counter, so neighbours of equal length and a short tail both pay.  Results do not depend on the
-        # order (every item owns its output row or its partial-sum slot).
-        lens = items[:, 2] - items[:, 1] if len(items) else np.zeros(0, dtype=np.int32)
-        if len(lens) and int(lens.max()) > 4 * max(float(lens.mean()), 1.0):
-            items = np.ascontiguousarray(items[np.argsort(-lens, kind="stable")])
+        if col_blocks > 1 and M.nnz:
+            items, long_rows, n_slots = plan_col_blocks(rowptr, M.indices, self.shape[1], int(col_blocks), int(chunk))
+        else:
+            items, long_rows, n_slots = capi.csr_plan(rowptr, int(chunk))
+            # Skewed row lengths (X^T's rows are term frequencies, power-law graphs have hubs): longest items first.
+            # The panel engine walks four to eight items per warp in lock step and the persistent engine pulls items
+            # from a counter, so neighbours of equal length and a short tail both pay.  Results do not depend on the
+            # order (every item owns its output row or its partial-sum slot).
+            lens = items[:, 2] - items[:, 1] if len(items) else np.zeros(0, dtype=np.int32)
+            if len(lens) and int(lens.max()) > 4 * max(float(lens.mean()), 1.0):
+                items = np.ascontiguousarray(items[np.argsort(-lens, kind="stable")])
+        self.col_blocks = int(col_blocks)
         self.rowptr = _pinned(rowptr)
         self.colidx = _pinned(np.ascontiguousarray(M.indices, dtype=np.int32))
         self.val = _pinned(np.ascontiguousarray(M.data, dtype=np.float32))
@@ -156,7 +215,8 @@ class HostGraph:
         self.XT = self.AT = None
         self.symmetric = True
         if need_backward:
-            self.XT = HostCsr(transpose_csr(Xl), chunk)
+            XTl = transpose_csr(Xl)
+            self.XT = HostCsr(XTl, chunk, col_blocks=panel_col_blocks(XTl.shape[1]))
             self.symmetric = bool(is_symmetric(A) if assume_symmetric is None else assume_symmetric)
             if not self.symmetric:
                 # A^T.G for a row block needs rows r0:r1 of A^T

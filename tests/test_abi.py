@@ -87,3 +87,45 @@ def test_csr_plan_items_cover_rows(built_library):
     # empty matrix
     items, long_rows, n_slots = capi.csr_plan(np.array([0], dtype=np.int32), 256)
     assert len(items) == 0 and len(long_rows) == 0 and n_slots == 0
+
+
+@pytest.mark.parametrize("n_blocks,chunk", [(1, 16), (2, 16), (2, 256), (3, 64), (4, 256)])
+def test_column_blocked_plan_covers_rows_without_straddling(built_library, n_blocks, chunk):
+    """plan_col_blocks: items tile every row in column order, never cross a column-range boundary, slots of a long
+    row are consecutive in column order, an empty row keeps one empty item; one block == the C planner."""
+    import scipy.sparse as sp
+    from geographconv_b200.engine import plan_col_blocks
+    rng = np.random.RandomState(0)
+    n_cols = 1000
+    M = sp.random(200, n_cols, density=0.05, random_state=rng, format="lil")
+    M[5, :] = 1
+    M[7, :] = 0
+    M = M.tocsr()
+    M.eliminate_zeros()
+    M.sort_indices()
+    items, long_rows, n_slots = plan_col_blocks(M.indptr, M.indices, n_cols, n_blocks, chunk)
+    bounds = np.array([(n_cols * k + n_blocks - 1) // n_blocks for k in range(n_blocks + 1)])
+    cover, slots = {}, []
+    for r, b, e, s in items.tolist():
+        assert 0 <= e - b <= chunk
+        cover.setdefault(r, []).append((b, e, s))
+        if e > b:
+            blk = np.searchsorted(bounds, M.indices[b:e], side="right") - 1
+            assert blk.min() == blk.max()
+    for r in range(M.shape[0]):
+        segs = sorted(cover[r])
+        assert segs[0][0] == M.indptr[r] and segs[-1][1] == M.indptr[r + 1]
+        assert all(a[1] == b[0] for a, b in zip(segs, segs[1:]))
+        if len(segs) == 1:
+            assert segs[0][2] == -1
+        else:
+            sl = [x[2] for x in segs]
+            assert sl == list(range(sl[0], sl[0] + len(sl)))
+            slots += sl
+    assert sorted(slots) == list(range(n_slots))
+    for r, s0, k in long_rows.tolist():
+        assert len(cover[r]) == k and sorted(cover[r])[0][2] == s0
+    if n_blocks == 1:
+        it0, lr0, ns0 = capi.csr_plan(np.ascontiguousarray(M.indptr, dtype=np.int32), chunk)
+        assert ns0 == n_slots and (lr0 == long_rows).all()
+        assert sorted(map(tuple, it0.tolist())) == sorted(map(tuple, items.tolist()))
