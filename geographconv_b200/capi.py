@@ -69,11 +69,14 @@ SIGNATURES = {
     "gcnb_spmm_workspace_bytes": (_sz, [C.POINTER(GcnbCsr), _i32]),
     "gcnb_gemm_f32": (C.c_int, [_ctxp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _i32]),
     "gcnb_gemm_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "gcnb_gemm_pair_f32": (C.c_int, [_ctxp, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _i32]),
     "gcnb_highway_fwd_f32": (C.c_int, [_ctxp, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _i32,
                                        _vp, _i32, _vp, _i32, _vp, _i32]),
     "gcnb_highway_workspace_bytes": (_sz, [_i32, _i32]),
     "gcnb_highway_bwd_f32": (C.c_int, [_ctxp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "gcnb_act_bwd_f32": (C.c_int, [_ctxp, _i32, _i32, _i32, _vp, _vp, _i32, _f32, _u64, _i64, _vp]),
+    "gcnb_highway_bwd_bias_f32": (C.c_int, [_ctxp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "gcnb_act_bwd_bias_f32": (C.c_int, [_ctxp, _i32, _i32, _i32, _vp, _vp, _i32, _f32, _u64, _i64, _vp, _vp]),
     "gcnb_colsum_f32": (C.c_int, [_ctxp, _i32, _i32, _vp, _i32, _vp, _i32]),
     "gcnb_colsum_workspace_bytes": (_sz, [_i32, _i32]),
     "gcnb_gather_rows_f32": (C.c_int, [_ctxp, _vp, _i32, _vp, _i32, _i32, _vp, _i32]),

@@ -17,6 +17,8 @@ int gcnb_gemm_tc(gcnb_ctx* ctx, int transB, int M, int N, int K, const float* A,
 bool gcnb_gemm_tc_supported(const gcnb_ctx* ctx, int transA, int transB, int M, int N, int K, int lda, int ldb,
                             int ldc, int accumulate);
 size_t gcnb_gemm_tc_workspace_bytes(int N, int K);
+int gcnb_gemm_pair_tc(gcnb_ctx* ctx, int transB, int M, int N, int K, const float* A1, int lda1, const float* B1, int ldb1,
+                      const float* A2, int lda2, const float* B2, int ldb2, float* C, int ldc, int accumulate);
 int gcnb_wgrad_tc(gcnb_ctx* ctx, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
                   int ldc, int accumulate);
 bool gcnb_wgrad_tc_supported(const gcnb_ctx* ctx, int M, int N, int K, int lda, int ldb);
@@ -223,6 +225,24 @@ extern "C" int gcnb_gemm_f32(gcnb_ctx* ctx, int32_t transA, int32_t transB, int3
   if (ctx->gemm_tc && gcnb_gemm_tc_supported(ctx, transA, transB, M, N, K, lda, ldb, ldc, accumulate))
     return gcnb_gemm_tc(ctx, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, act, accumulate);
   return gcnb_gemm_simt(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, accumulate, bias, act);
+}
+
+extern "C" int gcnb_gemm_pair_f32(gcnb_ctx* ctx, int32_t transB, int32_t M, int32_t N, int32_t K, const float* A1,
+                                  int32_t lda1, const float* B1, int32_t ldb1, const float* A2, int32_t lda2,
+                                  const float* B2, int32_t ldb2, float* C, int32_t ldc, int32_t accumulate) {
+  if (!ctx) return GCNB_E_INVALID;
+  GCNB_REQUIRE(ctx, A1 && B1 && A2 && B2 && C, "null matrix");
+  GCNB_REQUIRE(ctx, M >= 0 && N > 0 && K > 0, "bad shape");
+  GCNB_REQUIRE(ctx, lda1 >= K && lda2 >= K && ldb1 >= (transB ? K : N) && ldb2 >= (transB ? K : N) && ldc >= N,
+               "leading dimension too small");
+  if (M == 0) return GCNB_OK;
+  ProfScope scope(ctx, GCNB_TAG_GEMM);
+  if (ctx->gemm_tc && gcnb_gemm_tc_supported(ctx, 0, transB, M, N, K, lda1, ldb1, ldc, accumulate) &&
+      gcnb_gemm_tc_supported(ctx, 0, transB, M, N, K, lda2, ldb2, ldc, accumulate))
+    return gcnb_gemm_pair_tc(ctx, transB, M, N, K, A1, lda1, B1, ldb1, A2, lda2, B2, ldb2, C, ldc, accumulate);
+  int rc = gcnb_gemm_simt(ctx, 0, transB, M, N, K, A1, lda1, B1, ldb1, C, ldc, accumulate, nullptr, GCNB_ACT_LINEAR);
+  if (rc != GCNB_OK) return rc;
+  return gcnb_gemm_simt(ctx, 0, transB, M, N, K, A2, lda2, B2, ldb2, C, ldc, 1, nullptr, GCNB_ACT_LINEAR);
 }
 
 extern "C" size_t gcnb_highway_workspace_bytes(int32_t n_rows, int32_t hd) {

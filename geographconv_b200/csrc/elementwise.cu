@@ -108,12 +108,112 @@ __global__ void __launch_bounds__(kThreads) colsum_stage1_kernel(int n_rows, int
     __syncthreads();
   }
 }
-__global__ void colsum_stage2_kernel(int nblocks, int k, int nf4, const float* partial, float* out, int accumulate) {
+__global__ void colsum_stage2_kernel(int nblocks, int k, size_t stride, const float* partial, float* out, int accumulate) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= k) return;
   float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * nf4 * 4 + c];
+  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * stride + c];
   out[c] = accumulate ? out[c] + s : s;
+}
+
+// block-level column sum of per-thread float4 partials (8 warps x 32 lanes): warp 0 adds the 8 warps in order
+__device__ __forceinline__ void block_colsum_store(float4 (*red)[32], float4 s, int warp, int lane, bool on, float4* dst) {
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && on) {
+    float4 t = red[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) { t.x += red[w][lane].x; t.y += red[w][lane].y; t.z += red[w][lane].z; t.w += red[w][lane].w; }
+    *dst = t;
+  }
+  __syncthreads();
+}
+
+// highway backward fused with the two bias gradients: a warp owns whole rows (lanes over float4 columns), every
+// block keeps running column sums of dHpre and dTpre and writes them to partial[block][2][nf4*4]; stage 2 adds the
+// blocks in order (deterministic).  Saves re-reading dHpre and dTpre for gcnb_colsum_f32.
+template <int NCH>
+__global__ void __launch_bounds__(kThreads) highway_bwd_colsum_kernel(int n_rows, int nf4, int ld, const float* dY,
+                                                                      const float* X, const float* H, const float* T,
+                                                                      int act, float* dH, float* dT, float* dX,
+                                                                      float* partial) {
+  __shared__ float4 red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 sH[NCH], sT[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) sH[ch] = sT[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long r = (long long)blockIdx.x * 8 + warp; r < n_rows; r += (long long)gridDim.x * 8) {
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int c = lane + 32 * ch;
+      if (c < nf4) {
+        const float4 g = ld4(dY, (size_t)r, ld, c), x = ld4(X, (size_t)r, ld, c), h = ld4(H, (size_t)r, ld, c),
+                     t = ld4(T, (size_t)r, ld, c);
+        float4 dh, dt, dx;
+#define GCNB_HW_BWD(e)                                         \
+  dh.e = g.e * t.e * act_grad_from_out(act, h.e);              \
+  dt.e = g.e * (h.e - x.e) * t.e * (1.0f - t.e);               \
+  dx.e = g.e * (1.0f - t.e);                                   \
+  sH[ch].e += dh.e;                                            \
+  sT[ch].e += dt.e;
+        GCNB_HW_BWD(x) GCNB_HW_BWD(y) GCNB_HW_BWD(z) GCNB_HW_BWD(w)
+#undef GCNB_HW_BWD
+        st4(dH, (size_t)r, ld, c, dh);
+        st4(dT, (size_t)r, ld, c, dt);
+        st4(dX, (size_t)r, ld, c, dx);
+      }
+    }
+  }
+  float4* p4 = reinterpret_cast<float4*>(partial) + (size_t)blockIdx.x * 2 * nf4;
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int c = lane + 32 * ch;
+    block_colsum_store(red, sH[ch], warp, lane, c < nf4, p4 + c);
+    block_colsum_store(red, sT[ch], warp, lane, c < nf4, p4 + nf4 + c);
+  }
+}
+
+// activation / dropout backward fused with the bias gradient (column sums of dZ), same scheme
+template <int NCH>
+__global__ void __launch_bounds__(kThreads) act_bwd_colsum_kernel(int n_rows, int nf4, int ld, const float* dY,
+                                                                  const float* Yact, int act, uint32_t thresh, float scale,
+                                                                  uint64_t seed, int64_t row0, float* dZ, float* partial) {
+  __shared__ float4 red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 sZ[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) sZ[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float inv = 1.0f / scale;
+  for (long long r = (long long)blockIdx.x * 8 + warp; r < n_rows; r += (long long)gridDim.x * 8) {
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int c = lane + 32 * ch;
+      if (c < nf4) {
+        const float4 g = ld4(dY, (size_t)r, ld, c), y = ld4(Yact, (size_t)r, ld, c);
+        float4 o;
+        if (thresh != 0u) {
+          const uint4 d = dropout_draw(seed, row0 + (int64_t)r, (uint32_t)c);
+          o.x = d.x < thresh ? g.x * scale * act_grad_from_out(act, y.x * inv) : 0.f;
+          o.y = d.y < thresh ? g.y * scale * act_grad_from_out(act, y.y * inv) : 0.f;
+          o.z = d.z < thresh ? g.z * scale * act_grad_from_out(act, y.z * inv) : 0.f;
+          o.w = d.w < thresh ? g.w * scale * act_grad_from_out(act, y.w * inv) : 0.f;
+        } else {
+          o.x = g.x * act_grad_from_out(act, y.x);
+          o.y = g.y * act_grad_from_out(act, y.y);
+          o.z = g.z * act_grad_from_out(act, y.z);
+          o.w = g.w * act_grad_from_out(act, y.w);
+        }
+        sZ[ch].x += o.x; sZ[ch].y += o.y; sZ[ch].z += o.z; sZ[ch].w += o.w;
+        st4(dZ, (size_t)r, ld, c, o);
+      }
+    }
+  }
+  float4* p4 = reinterpret_cast<float4*>(partial) + (size_t)blockIdx.x * nf4;
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int c = lane + 32 * ch;
+    block_colsum_store(red, sZ[ch], warp, lane, c < nf4, p4 + c);
+  }
 }
 
 // cross-entropy metrics: one warp per gathered row
@@ -304,6 +404,81 @@ extern "C" int gcnb_highway_bwd_f32(gcnb_ctx* ctx, int32_t n_rows, int32_t hd, i
   return GCNB_OK;
 }
 
+extern "C" int gcnb_highway_bwd_bias_f32(gcnb_ctx* ctx, int32_t n_rows, int32_t hd, int32_t ld, const float* dY,
+                                         const float* X, const float* H, const float* T, int32_t act, float* dHpre,
+                                         float* dTpre, float* dX, float* dbh, float* dbt) {
+  if (!ctx) return GCNB_E_INVALID;
+  GCNB_REQUIRE(ctx, dY && X && H && T && dHpre && dTpre && dX && dbh && dbt, "null pointer");
+  GCNB_REQUIRE(ctx, ld % 4 == 0 && ld >= ((hd + 3) / 4) * 4, "ld: multiple of 4, >= hd rounded to 4");
+  const int nf4 = (hd + 3) / 4;
+  if (nf4 > 128) {  // wider than one warp pass covers: the unfused kernels
+    int rc = gcnb_highway_bwd_f32(ctx, n_rows, hd, ld, dY, X, H, T, act, dHpre, dTpre, dX);
+    if (rc == GCNB_OK) rc = gcnb_colsum_f32(ctx, n_rows, hd, dHpre, ld, dbh, 0);
+    if (rc == GCNB_OK) rc = gcnb_colsum_f32(ctx, n_rows, hd, dTpre, ld, dbt, 0);
+    return rc;
+  }
+  const size_t need = 2 * gcnb_colsum_workspace_bytes(n_rows, hd);
+  if (!ctx->ws || ctx->ws_bytes < need)
+    return gcnb_fail(ctx, GCNB_E_WORKSPACE, "highway_bwd_bias needs %s%lld workspace bytes, have %lld", "",
+                     (long long)need, (long long)ctx->ws_bytes);
+  ProfScope scope(ctx, GCNB_TAG_ELEM);
+  int blocks = cdiv(n_rows > 0 ? n_rows : 1, 64);
+  if (blocks > kMaxReduceBlocks) blocks = kMaxReduceBlocks;
+  float* partial = reinterpret_cast<float*>(ctx->ws);
+  const int nch = (nf4 + 31) / 32;
+#define GCNB_LAUNCH_HWB(N)                                                                                         \
+  highway_bwd_colsum_kernel<N><<<blocks, kThreads, 0, ctx->stream>>>(n_rows, nf4, ld, dY, X, H, T, act, dHpre, dTpre, \
+                                                                     dX, partial)
+  if (nch <= 1) GCNB_LAUNCH_HWB(1);
+  else if (nch == 2) GCNB_LAUNCH_HWB(2);
+  else if (nch == 3) GCNB_LAUNCH_HWB(3);
+  else GCNB_LAUNCH_HWB(4);
+#undef GCNB_LAUNCH_HWB
+  GCNB_LAUNCHED(ctx);
+  colsum_stage2_kernel<<<cdiv(hd, 128), 128, 0, ctx->stream>>>(blocks, hd, (size_t)nf4 * 8, partial, dbh, 0);
+  GCNB_LAUNCHED(ctx);
+  colsum_stage2_kernel<<<cdiv(hd, 128), 128, 0, ctx->stream>>>(blocks, hd, (size_t)nf4 * 8, partial + (size_t)nf4 * 4, dbt, 0);
+  GCNB_LAUNCHED(ctx);
+  return GCNB_OK;
+}
+
+extern "C" int gcnb_act_bwd_bias_f32(gcnb_ctx* ctx, int32_t n_rows, int32_t k, int32_t ld, const float* dY,
+                                     const float* Yact, int32_t act, float dropout_p, uint64_t seed, int64_t row0,
+                                     float* dZ, float* db) {
+  if (!ctx) return GCNB_E_INVALID;
+  GCNB_REQUIRE(ctx, dY && Yact && dZ && db, "null pointer");
+  GCNB_REQUIRE(ctx, ld % 4 == 0 && ld >= ((k + 3) / 4) * 4, "ld: multiple of 4, >= k rounded to 4");
+  GCNB_REQUIRE(ctx, dropout_p >= 0.f && dropout_p < 1.f, "dropout_p in [0,1)");
+  const int nf4 = (k + 3) / 4;
+  if (nf4 > 128) {
+    int rc = gcnb_act_bwd_f32(ctx, n_rows, k, ld, dY, Yact, act, dropout_p, seed, row0, dZ);
+    if (rc == GCNB_OK) rc = gcnb_colsum_f32(ctx, n_rows, k, dZ, ld, db, 0);
+    return rc;
+  }
+  const size_t need = gcnb_colsum_workspace_bytes(n_rows, k);
+  if (!ctx->ws || ctx->ws_bytes < need)
+    return gcnb_fail(ctx, GCNB_E_WORKSPACE, "act_bwd_bias needs %s%lld workspace bytes, have %lld", "",
+                     (long long)need, (long long)ctx->ws_bytes);
+  ProfScope scope(ctx, GCNB_TAG_ELEM);
+  int blocks = cdiv(n_rows > 0 ? n_rows : 1, 64);
+  if (blocks > kMaxReduceBlocks) blocks = kMaxReduceBlocks;
+  float* partial = reinterpret_cast<float*>(ctx->ws);
+  const float scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
+  const int nch = (nf4 + 31) / 32;
+#define GCNB_LAUNCH_AB(N)                                                                                      \
+  act_bwd_colsum_kernel<N><<<blocks, kThreads, 0, ctx->stream>>>(n_rows, nf4, ld, dY, Yact, act, thresh_of(dropout_p), \
+                                                                 scale, seed, row0, dZ, partial)
+  if (nch <= 1) GCNB_LAUNCH_AB(1);
+  else if (nch == 2) GCNB_LAUNCH_AB(2);
+  else if (nch == 3) GCNB_LAUNCH_AB(3);
+  else GCNB_LAUNCH_AB(4);
+#undef GCNB_LAUNCH_AB
+  GCNB_LAUNCHED(ctx);
+  colsum_stage2_kernel<<<cdiv(k, 128), 128, 0, ctx->stream>>>(blocks, k, (size_t)nf4 * 4, partial, db, 0);
+  GCNB_LAUNCHED(ctx);
+  return GCNB_OK;
+}
+
 extern "C" int gcnb_act_bwd_f32(gcnb_ctx* ctx, int32_t n_rows, int32_t k, int32_t ld, const float* dY,
                                 const float* Yact, int32_t act, float dropout_p, uint64_t seed, int64_t row0,
                                 float* dZ) {
@@ -342,7 +517,7 @@ extern "C" int gcnb_colsum_f32(gcnb_ctx* ctx, int32_t n_rows, int32_t k, const f
   float* partial = reinterpret_cast<float*>(ctx->ws);
   colsum_stage1_kernel<<<blocks, kThreads, 0, ctx->stream>>>(n_rows, nf4, A, lda, partial);
   GCNB_LAUNCHED(ctx);
-  colsum_stage2_kernel<<<cdiv(k, 128), 128, 0, ctx->stream>>>(blocks, k, nf4, partial, out, accumulate);
+  colsum_stage2_kernel<<<cdiv(k, 128), 128, 0, ctx->stream>>>(blocks, k, (size_t)nf4 * 4, partial, out, accumulate);
   GCNB_LAUNCHED(ctx);
   return GCNB_OK;
 }

@@ -41,7 +41,8 @@ struct alignas(64) TcParams {
   CUtensorMap mapBlo[2];  // weights, residual lo part, pre-split by split_weights_kernel
   CUtensorMap mapIn;      // X tile (highway) or C tile (accumulate): boxes of 32 columns x 128 rows
   CUtensorMap mapOut[3];  // plain: C; highway: Y, H, T
-  int nphase;      // 1: plain GEMM, 2: fused highway (phase 0 = S.Wh, phase 1 = X.Wt)
+  int nphase;      // k-loops: 1 = one product; 2 = two (highway: S.Wh and X.Wt; pair: A1.B1 + A2.B2)
+  int hw;          // 1: fused highway epilogue (two accumulators); 0: plain epilogue (one accumulator)
   int kblocks[2];  // 32-wide k-blocks per phase
   int M, N, BN, n_tiles;
   float* C;        // plain: output; highway: Y
@@ -189,9 +190,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     // of 16 dependent global loads per thread and chunk (4.8k of the 22k epilogue clocks, tools/gemm_phases.py)
     const int c = (int)threadIdx.x - 64, col = n0 + c;
     const bool on = c < BN && col < p.N && !(p.dbg_mode & 4);
-    const bool use_bias = p.nphase == 2 || (!p.accumulate && p.bias != nullptr);
+    const bool use_bias = p.hw || (!p.accumulate && p.bias != nullptr);
     bias_s[c] = (on && use_bias) ? __ldg(p.bias + col) : 0.f;
-    bias_s[kMaxBN + c] = (on && p.nphase == 2) ? __ldg(p.bias_t + col) : 0.f;
+    bias_s[kMaxBN + c] = (on && p.hw) ? __ldg(p.bias_t + col) : 0.f;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     int it = 0;
     long long w_conv = 0;
     for (int ph = 0; ph < p.nphase; ++ph) {
-      const uint32_t tacc = tmem_base + (uint32_t)(ph * BN);
+      const uint32_t tacc = tmem_base + (uint32_t)(p.hw ? ph * BN : 0);  // pair products share one accumulator
       for (int kb = 0; kb < p.kblocks[ph]; ++kb, ++it) {
         const int s = it % kStages;
         const uint32_t par = (it / kStages) & 1;
@@ -241,7 +242,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           // small terms first, then hi.hi
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k)
-            umma_tf32(tacc, umma_desc_k128(a_lo + 32 * k), umma_desc_k128(b_hi + 32 * k), idesc, (kb | k) != 0);
+            umma_tf32(tacc, umma_desc_k128(a_lo + 32 * k), umma_desc_k128(b_hi + 32 * k), idesc,
+                      (kb | k) != 0 || (ph != 0 && !p.hw));
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k)
             umma_tf32(tacc, umma_desc_k128(a_hi + 32 * k), umma_desc_k128(b_lo + 32 * k), idesc, 1u);
@@ -302,8 +304,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int grp = (warp - 2) >> 2;
     const int r = q * 32 + lane;       // row of the tile this thread owns
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-    const bool need_in = (p.nphase == 2) || p.accumulate;
-    const int n_out = p.nphase == 2 ? 3 : 1;
+    const bool need_in = p.hw || p.accumulate;
+    const int n_out = p.hw ? 3 : 1;
     unsigned char* in_base = smem;
     unsigned char* out_base = smem + (need_in ? (size_t)nch * kBox : 0) + (size_t)grp * n_out * kBox;
     if (need_in) {
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       first = false;
       unsigned char* ob = out_base + (size_t)r * 128;
       const float4* bs = reinterpret_cast<const float4*>(bias_s + ch * 32);
-      if (p.nphase == 1) {
+      if (!p.hw) {
         auto body = [&](auto act_fn) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -394,7 +396,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       if (leader && !(p.dbg_mode & 2)) {
         const uint32_t src = smem_u32(out_base);
         tma_store_2d(&p.mapOut[0], src, col0, m0);
-        if (p.nphase == 2) {
+        if (p.hw) {
           if (p.H) tma_store_2d(&p.mapOut[1], src + kBox, col0, m0);
           if (p.T) tma_store_2d(&p.mapOut[2], src + 2 * kBox, col0, m0);
         }
@@ -719,6 +721,44 @@ int gcnb_gemm_tc(gcnb_ctx* ctx, int transB, int M, int N, int K, const float* A,
   return launch(ctx, p);
 }
 
+// C (+)= A1.op(B1) + A2.op(B2) in one pass over C: two k-loops into one TMEM accumulator (the two dgrad products of
+// a highway layer, dx += dTpre.Wt^T + V.Wh^T: one read and one write of dx instead of two)
+int gcnb_gemm_pair_tc(gcnb_ctx* ctx, int transB, int M, int N, int K, const float* A1, int lda1, const float* B1, int ldb1,
+                      const float* A2, int lda2, const float* B2, int ldb2, float* C, int ldc, int accumulate) {
+  GCNB_REQUIRE(ctx, aligned16(A1) && aligned16(B1) && aligned16(A2) && aligned16(B2) && aligned16(C),
+               "tcgen05 gemm: 16-byte aligned matrices");
+  GCNB_REQUIRE(ctx, (ldc % 4) == 0, "tcgen05 gemm: ldc multiple of 4");
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  pick_bn(N, &p.BN, &p.n_tiles);
+  const size_t need = 2 * gcnb_gemm_tc_workspace_bytes(N, K);
+  if (!ctx->ws || ctx->ws_bytes < need)
+    return gcnb_fail(ctx, GCNB_E_WORKSPACE, "tcgen05 gemm pair needs %s%lld workspace bytes, have %lld", "",
+                     (long long)need, (long long)ctx->ws_bytes);
+  const int ldbt = ld32(K);
+  const size_t wsz = (size_t)N * ldbt;
+  float* Bt1 = reinterpret_cast<float*>(ctx->ws);
+  float* Blo1 = Bt1 + wsz;
+  float* Bt2 = Blo1 + wsz;
+  float* Blo2 = Bt2 + wsz;
+  int rc = split_weights(ctx, B1, ldb1, K, N, transB ? 0 : 1, Bt1, Blo1, ldbt);
+  if (rc != GCNB_OK) return rc;
+  rc = split_weights(ctx, B2, ldb2, K, N, transB ? 0 : 1, Bt2, Blo2, ldbt);
+  if (rc != GCNB_OK) return rc;
+  if (!make_map(&p.mapA[0], A1, M, K, lda1, BM) || !make_map(&p.mapB[0], Bt1, N, K, ldbt, p.BN) ||
+      !make_map(&p.mapBlo[0], Blo1, N, K, ldbt, p.BN) || !make_map(&p.mapA[1], A2, M, K, lda2, BM) ||
+      !make_map(&p.mapB[1], Bt2, N, K, ldbt, p.BN) || !make_map(&p.mapBlo[1], Blo2, N, K, ldbt, p.BN))
+    return gcnb_fail(ctx, GCNB_E_CUDA, "cuTensorMapEncodeTiled failed%s", "");
+  if (!make_map(&p.mapOut[0], C, M, N, ldc, BM) || (accumulate && !make_map(&p.mapIn, C, M, N, ldc, BM)))
+    return gcnb_fail(ctx, GCNB_E_CUDA, "cuTensorMapEncodeTiled failed%s", "");
+  p.nphase = 2;
+  p.hw = 0;
+  p.kblocks[0] = p.kblocks[1] = cdiv(K, BK);
+  p.M = M; p.N = N;
+  p.C = C; p.ldc = ldc; p.bias = nullptr; p.act = GCNB_ACT_LINEAR; p.accumulate = accumulate;
+  return launch(ctx, p);
+}
+
 bool gcnb_highway_tc_supported(const gcnb_ctx* ctx, int n_rows, int hd, int lds, int ldx, int ldwh, int ldwt) {
   (void)ctx;
   if (n_rows < 1 || hd < 1) return false;
@@ -760,6 +800,7 @@ int gcnb_highway_tc(gcnb_ctx* ctx, int n_rows, int hd, const float* S, int lds, 
       (H && !make_map(&p.mapOut[1], H, n_rows, hd, ldh, BM)) || (T && !make_map(&p.mapOut[2], T, n_rows, hd, ldt, BM)))
     return gcnb_fail(ctx, GCNB_E_CUDA, "cuTensorMapEncodeTiled failed%s", "");
   p.nphase = 2;
+  p.hw = 1;
   p.kblocks[0] = p.kblocks[1] = cdiv(hd, BK);
   p.M = n_rows; p.N = hd;
   p.C = Y; p.ldc = ldy; p.bias = bh; p.act = act; p.accumulate = 0;

@@ -417,9 +417,11 @@ __device__ __forceinline__ void panel_epilogue(const SpmmParams& p, int row, int
   st_stream_f4(cptr, o);
 }
 
-// GL lanes per row item (panel = 4*GL floats), R (column, value) pairs per lane and batch: GL*R gathers in flight
-template <int GL, int R>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_panel_kernel(const SpmmParams p) {
+// GL lanes per row item (panel = 4*GL floats), R (column, value) pairs per lane and batch: GL*R gathers in flight.
+// KEEP: gathers carry an L2 evict_last hint.  Batches in which every item of the warp still has GL*R nonzeros run
+// without predicates (plans sorted by item length make that the common case); the rest take the predicated tail.
+template <int GL, int R, bool KEEP>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, GL * R <= 8 ? 4 : 2) spmm_panel_kernel(const SpmmParams p) {
   constexpr int G = 32 / GL;
   constexpr int NB = GL * R;
   const int lane = threadIdx.x & 31;
@@ -431,14 +433,60 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_panel_kernel(const Spm
   if (valid) it = __ldg(p.items + item);
   const int n = it.z - it.y;
   const int nmax = __reduce_max_sync(0xffffffffu, n);
+  const int nmin = __reduce_min_sync(0xffffffffu, n);
   const bool lane_on = col0 + 4 * gl < p.k4;
   const uint64_t pol = policy_evict_first();
   const uint64_t keep = policy_evict_last();
-  const float4* Bs = reinterpret_cast<const float4*>(p.B + col0) + gl;
-  const size_t ldb4 = (size_t)(p.ldb >> 2);
+  // lanes past the last column of a partial panel gather the panel's first float4 instead (in bounds) and never store
+  const char* Bs = reinterpret_cast<const char*>(p.B + col0 + (lane_on ? 4 * gl : 0));
+  const uint32_t row_bytes = (uint32_t)p.ldb * 4u;
+  const int* colp = p.col + it.y + gl;
+  const float* valp = p.val + it.y + gl;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  for (int base = 0; base < nmax; base += NB) {
+  auto gather = [&](int cj) -> float4 {
+    const float4* src = reinterpret_cast<const float4*>(Bs + (uint64_t)(uint32_t)cj * row_bytes);
+    return KEEP ? ld_gather_hint_f4(src, keep) : ld_gather_f4(src);
+  };
+
+  int base = 0;
+  if (NB <= nmin) {  // batches every lane group can fill: no predicates; (column, value) pairs fetched one batch ahead
+    int c[R], cn[R];
+    float a[R], an[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      c[r] = ld_stream_s32(colp + r * GL, pol);
+      a[r] = ld_stream_f32(valp + r * GL, pol);
+      cn[r] = 0;
+      an[r] = 0.f;
+    }
+    for (; base + NB <= nmin; base += NB) {
+      if (base + 2 * NB <= nmin) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          cn[r] = ld_stream_s32(colp + base + NB + r * GL, pol);
+          an[r] = ld_stream_f32(valp + base + NB + r * GL, pol);
+        }
+      }
+      float4 x[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) x[j] = gather(__shfl_sync(0xffffffffu, c[j / GL], j % GL, GL));
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const float aj = __shfl_sync(0xffffffffu, a[j / GL], j % GL, GL);
+        acc.x = fmaf(aj, x[j].x, acc.x);
+        acc.y = fmaf(aj, x[j].y, acc.y);
+        acc.z = fmaf(aj, x[j].z, acc.z);
+        acc.w = fmaf(aj, x[j].w, acc.w);
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        c[r] = cn[r];
+        a[r] = an[r];
+      }
+    }
+  }
+  for (; base < nmax; base += NB) {  // ragged tail: per-item predicates
     int c[R];
     float a[R];
 #pragma unroll
@@ -447,8 +495,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_panel_kernel(const Spm
       c[r] = 0;
       a[r] = 0.f;
       if (k < n) {
-        c[r] = ld_stream_s32(p.col + it.y + k, pol);
-        a[r] = ld_stream_f32(p.val + it.y + k, pol);
+        c[r] = ld_stream_s32(colp + base + r * GL, pol);
+        a[r] = ld_stream_f32(valp + base + r * GL, pol);
       }
     }
     float4 x[NB];
@@ -456,10 +504,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_panel_kernel(const Spm
     for (int j = 0; j < NB; ++j) {
       const int cj = __shfl_sync(0xffffffffu, c[j / GL], j % GL, GL);
       x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (lane_on && base + j < n) {
-        const float4* src = Bs + (size_t)cj * ldb4;
-        x[j] = p.evict_last ? ld_gather_hint_f4(src, keep) : ld_gather_f4(src);
-      }
+      if (base + j < n) x[j] = gather(cj);
     }
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
@@ -602,15 +647,21 @@ int launch_panels(gcnb_ctx* ctx, const SpmmParams& p0, int n_rows, int K4, int u
     const int GL = PW / 4, G = 32 / GL;
     const dim3 grid(cdiv(p.n_items, kWarpsPerCta * G), cdiv(K4, PW));
     const int threads = kWarpsPerCta * 32;
+#define GCNB_PANEL(GLV, RV)                                                                   \
+  do {                                                                                        \
+    if (p.evict_last) spmm_panel_kernel<GLV, RV, true><<<grid, threads, 0, ctx->stream>>>(p); \
+    else spmm_panel_kernel<GLV, RV, false><<<grid, threads, 0, ctx->stream>>>(p);             \
+  } while (0)
     if (GL == 4) {
-      if (unroll >= 16) spmm_panel_kernel<4, 4><<<grid, threads, 0, ctx->stream>>>(p);
-      else spmm_panel_kernel<4, 2><<<grid, threads, 0, ctx->stream>>>(p);
+      if (unroll >= 16) GCNB_PANEL(4, 4);
+      else GCNB_PANEL(4, 2);
     } else if (GL == 8) {
-      if (unroll >= 16) spmm_panel_kernel<8, 2><<<grid, threads, 0, ctx->stream>>>(p);
-      else spmm_panel_kernel<8, 1><<<grid, threads, 0, ctx->stream>>>(p);
+      if (unroll >= 16) GCNB_PANEL(8, 2);
+      else GCNB_PANEL(8, 1);
     } else {
-      spmm_panel_kernel<16, 1><<<grid, threads, 0, ctx->stream>>>(p);
+      GCNB_PANEL(16, 1);
     }
+#undef GCNB_PANEL
     GCNB_LAUNCHED(ctx);
   }
   for (int pass = 0; pass < 2; ++pass) {  // 0: long-row fix-up, 1: row softmax

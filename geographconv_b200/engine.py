@@ -129,12 +129,12 @@ class HostCsr:
             items, long_rows, n_slots = plan_col_blocks(rowptr, M.indices, self.shape[1], int(col_blocks), int(chunk))
         else:
             items, long_rows, n_slots = capi.csr_plan(rowptr, int(chunk))
-            # Skewed row lengths (X^T's rows are term frequencies, power-law graphs have hubs): longest items first.
-            # The panel engine walks four to eight items per warp in lock step and the persistent engine pulls items
-            # from a counter, so neighbours of equal length and a short tail both pay.  Results do not depend on the
+            # Longest items first.  The panel engine walks four to eight items per warp in lock step and only its
+            # predicate-free fast path is cheap (8 instructions per gathered float4), so neighbours of equal length pay;
+            # the persistent engine pulls items from a counter, so a short tail pays.  Results do not depend on the
             # order (every item owns its output row or its partial-sum slot).
             lens = items[:, 2] - items[:, 1] if len(items) else np.zeros(0, dtype=np.int32)
-            if len(lens) and int(lens.max()) > 4 * max(float(lens.mean()), 1.0):
+            if len(lens) and int(lens.max()) > int(lens.min()):
                 items = np.ascontiguousarray(items[np.argsort(-lens, kind="stable")])
         self.col_blocks = int(col_blocks)
         self.rowptr = _pinned(rowptr)
@@ -519,7 +519,7 @@ class Engine:
         need = max(need, self.lib.gcnb_spmm_workspace_bytes(C.byref(self.X.struct), hd))
         need = max(need, self.lib.gcnb_highway_workspace_bytes(0, max(widths)))
         wall = max(widths + [L.output_size, hd])
-        need = max(need, self.lib.gcnb_gemm_workspace_bytes(0, max(n, 1), wall, wall))
+        need = max(need, 2 * self.lib.gcnb_gemm_workspace_bytes(0, max(n, 1), wall, wall))
         self.W0_hot = None
         if self.kh:
             self.W0_hot = self._zeros(self.kh, self.ldh[0])   # W0[hot, :] forward, dW0[hot, :] backward
@@ -530,7 +530,7 @@ class Engine:
             need = max(need, self.lib.gcnb_spmm_workspace_bytes(C.byref(self.XT.struct), hd))
             wmax = max(widths + [L.output_size])
             need = max(need, self.lib.gcnb_gemm_workspace_bytes(1, wmax, wmax, max(n, 1)))
-            need = max(need, self.lib.gcnb_colsum_workspace_bytes(n, wmax))
+            need = max(need, 2 * self.lib.gcnb_colsum_workspace_bytes(n, wmax))
         self._ensure_ws(need)
         self._fence()
 
@@ -726,32 +726,35 @@ class Engine:
             if l["kind"] == "hw":
                 dH = self.dH.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
                 dT = self.dT.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
-                # dHpre, dTpre, dx*(1-t) (in place over dX)
-                self.ctx.call("gcnb_highway_bwd_f32", n, n_out, ldy, _ptr(dX), _ptr(xin), _ptr(b["H"]), _ptr(b["T"]),
-                              self.act, _ptr(dH), _ptr(dT), _ptr(dX))
-                pending = self._conv_begin(dH, n_out)
-                V = self.U.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
                 gWh, ldgh = self._gptr("Wh%d" % k)
                 gbh, _ = self._gptr("bh%d" % k)
                 gWt, ldgt = self._gptr("Wt%d" % k)
                 gbt, _ = self._gptr("bt%d" % k)
+                # dHpre, dTpre, dx*(1-t) (in place over dX) and both bias gradients in one pass
+                self.ctx.call("gcnb_highway_bwd_bias_f32", n, n_out, ldy, _ptr(dX), _ptr(xin), _ptr(b["H"]),
+                              _ptr(b["T"]), self.act, _ptr(dH), _ptr(dT), _ptr(dX), gbh, gbt)
+                pending = self._conv_begin(dH, n_out)
+                V = self.U.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
                 Wh, ldwh = self._pptr("Wh%d" % k)
                 Wt, ldwt = self._pptr("Wt%d" % k)
                 # everything that does not need V = A^T.dHpre runs while its operand is being exchanged
-                self.ctx.call("gcnb_colsum_f32", n, n_out, _ptr(dH), ldy, gbh, 0)
                 self._gemm(1, 0, n_in, n_out, n, xin, ldin, dT, ldy, gWt, ldgt)     # dWt = x^T.dTpre
-                self.ctx.call("gcnb_colsum_f32", n, n_out, _ptr(dT), ldy, gbt, 0)
-                self._gemm(0, 1, n, n_in, n_out, dT, ldy, Wt, ldwt, dX, ldin, accumulate=1)  # dx += dTpre.Wt^T
+                if self.world > 1:  # keeps the exchange of dHpre covered
+                    self._gemm(0, 1, n, n_in, n_out, dT, ldy, Wt, ldwt, dX, ldin, accumulate=1)  # dx += dTpre.Wt^T
                 self._conv_finish(pending, csrT, V, ldy, n_out)                     # V = A^T.dHpre
                 self._gemm(1, 0, n_in, n_out, n, xin, ldin, V, ldy, gWh, ldgh)      # dWh = x^T.V
-                self._gemm(0, 1, n, n_in, n_out, V, ldy, Wh, ldwh, dX, ldin, accumulate=1)   # dx += V.Wh^T
+                if self.world > 1:
+                    self._gemm(0, 1, n, n_in, n_out, V, ldy, Wh, ldwh, dX, ldin, accumulate=1)   # dx += V.Wh^T
+                elif n > 0:  # one pass over dx: dx += dTpre.Wt^T + V.Wh^T
+                    self.ctx.call("gcnb_gemm_pair_f32", 1, n, n_in, n_out, _ptr(dT), ldy, Wt, ldwt, _ptr(V), ldy, Wh,
+                                  ldwh, _ptr(dX), ldin, 1)
             else:
                 dP = self.dH.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
-                self.ctx.call("gcnb_act_bwd_f32", n, n_out, ldy, _ptr(dX), _ptr(b["Y"]), self.act, 0.0, 0, 0, _ptr(dP))
+                gb, _ = self._gptr("b%d" % k)
+                self.ctx.call("gcnb_act_bwd_bias_f32", n, n_out, ldy, _ptr(dX), _ptr(b["Y"]), self.act, 0.0, 0, 0,
+                              _ptr(dP), gb)
                 pending = self._conv_begin(dP, n_out)
                 V = self.U.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
-                gb, _ = self._gptr("b%d" % k)
-                self.ctx.call("gcnb_colsum_f32", n, n_out, _ptr(dP), ldy, gb, 0)
                 self._conv_finish(pending, csrT, V, ldy, n_out)
                 gW, ldgw = self._gptr("W%d" % k)
                 W, ldw = self._pptr("W%d" % k)
@@ -763,17 +766,16 @@ class Engine:
         ld0 = self.ldh[0]
         dX = self.dX.view(-1)[: self.nbuf * ld0].view(self.nbuf, ld0)
         p = self.drop_out
-        self.ctx.call("gcnb_act_bwd_f32", n, hd, ld0, _ptr(dX), _ptr(self.H0), self.act, p, int(seed) & (2**64 - 1),
-                      int(self.r0), _ptr(dX))
         gW0, ldg0 = self._gptr("W0")
         gb0, _ = self._gptr("b0")
+        self.ctx.call("gcnb_act_bwd_bias_f32", n, hd, ld0, _ptr(dX), _ptr(self.H0), self.act, p, int(seed) & (2**64 - 1),
+                      int(self.r0), _ptr(dX), gb0)
         self._wait_upload("XT")
         self._spmm(self.XT, dX, ld0, gW0, ldg0, hd)                                 # dW0 = X^T.dz (cold columns)
         if self.kh:                                                                 # hot columns: dense wgrad
             self._gemm(1, 0, self.kh, hd, n, self.X_hot, self.kh, dX, ld0, self.W0_hot, self.ldh[0])
             self.ctx.call("gcnb_scatter_rows_f32", _ptr(self.W0_hot), self.ldh[0], _ptr(self.hot_idx), self.kh, hd,
                           gW0, ldg0)
-        self.ctx.call("gcnb_colsum_f32", n, hd, _ptr(dX), ld0, gb0, 0)
         if self.world > 1:
             with torch.cuda.stream(self.stream):
                 torch.distributed.all_reduce(self.grads, group=self.group)

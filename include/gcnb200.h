@@ -158,6 +158,12 @@ int gcnb_gemm_f32(gcnb_ctx* ctx, int32_t transA, int32_t transB, int32_t M, int3
                   const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc,
                   int32_t accumulate, const float* bias, int32_t act);
 size_t gcnb_gemm_workspace_bytes(int32_t transA, int32_t M, int32_t N, int32_t K);
+/* C[M x N] (+)= A1 . op(B1) + A2 . op(B2), both products M x K by K x N, in one pass over C (two k-loops into one
+ * accumulator): the two dgrad products of a highway layer, dx += dTpre.Wt^T + V.Wh^T (gradient of gcnmodel.py:126,285).
+ * Workspace: 2 x gcnb_gemm_workspace_bytes(0, M, N, K). */
+int gcnb_gemm_pair_f32(gcnb_ctx* ctx, int32_t transB, int32_t M, int32_t N, int32_t K, const float* A1, int32_t lda1,
+                       const float* B1, int32_t ldb1, const float* A2, int32_t lda2, const float* B2, int32_t ldb2,
+                       float* C, int32_t ldc, int32_t accumulate);
 
 /* The fused highway layer (north-star op):  h = act(S.Wh + bh), t = sigmoid(X.Wt + bt),
  * Y = t*h + (1-t)*X, with S = A_hat.X computed beforehand by gcnb_spmm_csr_f32.
@@ -175,11 +181,22 @@ int gcnb_highway_bwd_f32(gcnb_ctx* ctx, int32_t n_rows, int32_t hd, int32_t ld, 
                          const float* X, const float* H, const float* T, int32_t act,
                          float* dHpre, float* dTpre, float* dX);
 
+/* the same plus the two bias gradients dbh[k] = sum_rows dHpre[:, k], dbt[k] = sum_rows dTpre[:, k] (deterministic),
+ * fused so that dHpre / dTpre are not read again for gcnb_colsum_f32.  Workspace: 2 x gcnb_colsum_workspace_bytes. */
+int gcnb_highway_bwd_bias_f32(gcnb_ctx* ctx, int32_t n_rows, int32_t hd, int32_t ld, const float* dY,
+                              const float* X, const float* H, const float* T, int32_t act,
+                              float* dHpre, float* dTpre, float* dX, float* dbh, float* dbt);
+
 /* dZ = dY * keep*scale * act'(a), where Yact holds dropout(act(z)) (first layer,
  * gcnmodel.py:353-357) or act(z) when dropout_p == 0.  In-place (dZ == dY) allowed. */
 int gcnb_act_bwd_f32(gcnb_ctx* ctx, int32_t n_rows, int32_t k, int32_t ld, const float* dY,
                      const float* Yact, int32_t act, float dropout_p, uint64_t seed, int64_t row0,
                      float* dZ);
+
+/* gcnb_act_bwd_f32 plus db[k] = sum_rows dZ[:, k] in the same pass (workspace: gcnb_colsum_workspace_bytes) */
+int gcnb_act_bwd_bias_f32(gcnb_ctx* ctx, int32_t n_rows, int32_t k, int32_t ld, const float* dY,
+                          const float* Yact, int32_t act, float dropout_p, uint64_t seed, int64_t row0,
+                          float* dZ, float* db);
 
 /* out[k] (+)= sum over rows of A[:, k]  (bias gradients).  Deterministic. */
 int gcnb_colsum_f32(gcnb_ctx* ctx, int32_t n_rows, int32_t k, const float* A, int32_t lda,

@@ -252,3 +252,76 @@ def test_highway_forward(n, hd, tc):
     _close(H, h, atol_scale=2e-5)
     _close(T, t, atol_scale=2e-5)
     _close(Y, t * h + (1 - t) * X, atol_scale=2e-5)
+
+
+@pytest.mark.parametrize("n,k", [(1000, 300), (777, 129), (5000, 512), (64, 7), (300, 600)])
+def test_fused_backward_with_bias_gradients(n, k):
+    """gcnb_highway_bwd_bias_f32 / gcnb_act_bwd_bias_f32: element-wise outputs identical to the unfused kernels,
+    bias gradients = column sums (float64 reference), run-to-run identical."""
+    import ctypes as C
+    import torch
+    from geographconv_b200.layers import get_dev
+    from geographconv_b200.partition import ld_of
+    d = get_dev()
+    rng = np.random.RandomState(n + k)
+    ld = ld_of(k)
+    host = {name: rng.randn(n, k).astype(np.float32) for name in ("dY", "X")}
+    host["H"] = np.tanh(rng.randn(n, k)).astype(np.float32)
+    host["T"] = (1 / (1 + np.exp(-rng.randn(n, k)))).astype(np.float32)
+    dev = {name: d.dense(v)[0] for name, v in host.items()}
+    outs = {name: torch.zeros(n * ld, dtype=torch.float32, device=d.dev) for name in
+            ("dH", "dT", "dX", "dH2", "dT2", "dX2", "dZ", "dZ2")}
+    db = {name: torch.zeros(ld, dtype=torch.float32, device=d.dev) for name in ("bh", "bt", "bz", "bh_again")}
+    d.ensure_ws(2 * d.ctx.lib.gcnb_colsum_workspace_bytes(n, k))
+    p = lambda t: C.c_void_p(t.data_ptr())
+    d.fence()
+    d.ctx.call("gcnb_highway_bwd_f32", n, k, ld, p(dev["dY"]), p(dev["X"]), p(dev["H"]), p(dev["T"]), 1, p(outs["dH"]),
+               p(outs["dT"]), p(outs["dX"]))
+    d.ctx.call("gcnb_highway_bwd_bias_f32", n, k, ld, p(dev["dY"]), p(dev["X"]), p(dev["H"]), p(dev["T"]), 1,
+               p(outs["dH2"]), p(outs["dT2"]), p(outs["dX2"]), p(db["bh"]), p(db["bt"]))
+    d.ctx.call("gcnb_highway_bwd_bias_f32", n, k, ld, p(dev["dY"]), p(dev["X"]), p(dev["H"]), p(dev["T"]), 1,
+               p(outs["dH2"]), p(outs["dT2"]), p(outs["dX2"]), p(db["bh_again"]), p(db["bt"]))
+    seed, row0, pdrop = 99, 7, 0.5
+    d.ctx.call("gcnb_act_bwd_f32", n, k, ld, p(dev["dY"]), p(dev["H"]), 1, pdrop, seed, row0, p(outs["dZ"]))
+    d.ctx.call("gcnb_act_bwd_bias_f32", n, k, ld, p(dev["dY"]), p(dev["H"]), 1, pdrop, seed, row0, p(outs["dZ2"]), p(db["bz"]))
+    got = {name: d.download(t, n, ld, k) for name, t in outs.items()}
+    gb = {name: d.download(t, 1, ld, k)[0] for name, t in db.items()}
+    for a in ("dH", "dT", "dX", "dZ"):
+        np.testing.assert_array_equal(got[a], got[a + "2"])
+    g, x, h, t = (host[q].astype(np.float64) for q in ("dY", "X", "H", "T"))
+    _close(got["dH"], g * t * (1 - h * h))
+    _close(got["dT"], g * (h - x) * t * (1 - t))
+    _close(got["dX"], g * (1 - t))
+    for name, ref in (("bh", got["dH"]), ("bt", got["dT"]), ("bz", got["dZ"])):
+        want = ref.astype(np.float64).sum(0)
+        np.testing.assert_allclose(gb[name], want, rtol=1e-4, atol=1e-4 * np.abs(ref).sum(0).max())
+    np.testing.assert_array_equal(gb["bh"], gb["bh_again"])
+
+
+@pytest.mark.parametrize("M,N,K,acc", [(1000, 300, 300, 1), (257, 300, 300, 0), (4000, 129, 512, 1)])
+def test_gemm_pair_one_pass(M, N, K, acc):
+    """gcnb_gemm_pair_f32: C (+)= A1.B1^T + A2.B2^T with both k-loops in one tcgen05 kernel (fp32-grade, 3xTF32)."""
+    import ctypes as C
+    import torch
+    from geographconv_b200.layers import get_dev
+    d = get_dev()
+    rng = np.random.RandomState(M + N)
+    A1, A2 = rng.randn(M, K).astype(np.float32), rng.randn(M, K).astype(np.float32)
+    B1, B2 = rng.randn(N, K).astype(np.float32), rng.randn(N, K).astype(np.float32)  # used transposed (dgrad: W is (in, out))
+    C0 = rng.randn(M, N).astype(np.float32)
+    dA1, lda = d.dense(A1)
+    dA2, _ = d.dense(A2)
+    dB1, ldb = d.dense(B1)
+    dB2, _ = d.dense(B2)
+    dC, ldc = d.dense(C0)
+    d.ensure_ws(2 * d.ctx.lib.gcnb_gemm_workspace_bytes(0, M, N, K))
+    p = lambda t: C.c_void_p(t.data_ptr())
+    d.fence()
+    before = d.ctx.get_option("tc_launches")
+    d.ctx.call("gcnb_gemm_pair_f32", 1, M, N, K, p(dA1), lda, p(dB1), ldb, p(dA2), lda, p(dB2), ldb, p(dC), ldc, acc)
+    got = d.download(dC, M, ldc, N)
+    assert d.ctx.get_option("tc_launches") == before + 1
+    want = A1.astype(np.float64) @ B1.astype(np.float64).T + A2.astype(np.float64) @ B2.astype(np.float64).T
+    if acc:
+        want = want + C0
+    _close(got, want, atol_scale=3e-6)
