@@ -79,11 +79,13 @@ SIGNATURES = {
     "gcnb_act_bwd_bias_f32": (C.c_int, [_ctxp, _i32, _i32, _i32, _vp, _vp, _i32, _f32, _u64, _i64, _vp, _vp]),
     "gcnb_colsum_f32": (C.c_int, [_ctxp, _i32, _i32, _vp, _i32, _vp, _i32]),
     "gcnb_colsum_workspace_bytes": (_sz, [_i32, _i32]),
+    "gcnb_csr_to_dense_f32": (C.c_int, [_ctxp, _vp, _vp, _vp, _i32, _i32, _vp, _i32]),
     "gcnb_gather_rows_f32": (C.c_int, [_ctxp, _vp, _i32, _vp, _i32, _i32, _vp, _i32]),
     "gcnb_scatter_rows_f32": (C.c_int, [_ctxp, _vp, _i32, _vp, _i32, _i32, _vp, _i32]),
     "gcnb_xent_metrics_f32": (C.c_int, [_ctxp, _vp, _i32, _i32, _vp, _vp, _i32, _vp]),
     "gcnb_xent_grad_f32": (C.c_int, [_ctxp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _f32, _vp, _i32]),
     "gcnb_gather_argmax_f32": (C.c_int, [_ctxp, _vp, _i32, _i32, _vp, _i32, _vp, _vp]),
+    "gcnb_geo_distance_f64": (C.c_int, [_ctxp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, C.c_double, _vp, _vp]),
     "gcnb_l1l2_f32": (C.c_int, [_ctxp, _vp, _vp, _i64, _f32, _vp]),
     "gcnb_adam_f32": (C.c_int, [_ctxp, _vp, _vp, _vp, _vp, _i64, _vp, _f32, _f32, _f32, _f32]),
     "gcnb_dropout_mask_u8": (C.c_int, [_ctxp, _i32, _i32, _f32, _u64, _i64, _vp]),

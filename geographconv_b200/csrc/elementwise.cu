@@ -353,6 +353,17 @@ __global__ void dropout_mask_kernel(int n_rows, int k, uint32_t thresh, uint64_t
 }
 
 // dst[i] = src[idx[i]] (gather) or dst[idx[i]] = src[i] (scatter), float4 rows
+// dense[r, col[k]] = val[k] for the nonzeros k of CSR row r (warp per row; dense was cleared beforehand)
+__global__ void __launch_bounds__(kThreads) csr_to_dense_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+                                                                const float* __restrict__ val, int n_rows, float* dense,
+                                                                int ld) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= n_rows) return;
+  float* out = dense + (size_t)r * ld;
+  for (int k = rowptr[r] + lane; k < rowptr[r + 1]; k += 32) out[col[k]] = val[k];
+}
+
 __global__ void move_rows_kernel(const float* src, int ld_src, const int* idx, int n_idx, int nf4, float* dst,
                                  int ld_dst, int scatter) {
   const long long total = (long long)n_idx * nf4;
@@ -622,6 +633,19 @@ static int move_rows(gcnb_ctx* ctx, const float* src, int ld_src, const int* idx
   GCNB_LAUNCHED(ctx);
   return GCNB_OK;
 }
+extern "C" int gcnb_csr_to_dense_f32(gcnb_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, const float* val,
+                                     int32_t n_rows, int32_t n_cols, float* dense, int32_t ld) {
+  if (!ctx) return GCNB_E_INVALID;
+  GCNB_REQUIRE(ctx, n_rows >= 0 && n_cols >= 0 && ld >= n_cols, "bad shape");
+  if (n_rows == 0 || n_cols == 0) return GCNB_OK;
+  GCNB_REQUIRE(ctx, rowptr && dense, "null pointer");
+  ProfScope scope(ctx, GCNB_TAG_COPY);
+  GCNB_CUDA(ctx, cudaMemsetAsync(dense, 0, (size_t)n_rows * ld * sizeof(float), ctx->stream));
+  csr_to_dense_kernel<<<cdiv(n_rows, 8), kThreads, 0, ctx->stream>>>(rowptr, colidx, val, n_rows, dense, ld);
+  GCNB_LAUNCHED(ctx);
+  return GCNB_OK;
+}
+
 extern "C" int gcnb_gather_rows_f32(gcnb_ctx* ctx, const float* src, int32_t ld_src, const int32_t* idx, int32_t n_idx,
                                     int32_t k, float* dst, int32_t ld_dst) {
   return move_rows(ctx, src, ld_src, idx, n_idx, k, dst, ld_dst, 0);

@@ -164,7 +164,7 @@ extern "C" size_t gcnb_gemm_workspace_bytes(int32_t transA, int32_t M, int32_t N
   const int s = pick_splits(M, N, K);
   const size_t simt = s <= 1 ? 0 : (size_t)s * M * N * sizeof(float);
   // tcgen05 paths: transposed weight copy (activation x weight) or split-K partial tiles (wgrad)
-  const size_t tc = transA ? (M <= 1024 && N <= 1024 ? gcnb_wgrad_tc_workspace_bytes(M, N, K) : 0)
+  const size_t tc = transA ? (M <= 4096 && N <= 4096 ? gcnb_wgrad_tc_workspace_bytes(M, N, K) : 0)
                            : gcnb_gemm_tc_workspace_bytes(N, K);
   return simt > tc ? simt : tc;
 }

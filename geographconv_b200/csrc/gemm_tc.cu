@@ -833,7 +833,7 @@ WgPlan wgrad_plan(int sm_count, int M, int N, int K) {
 bool gcnb_wgrad_tc_supported(const gcnb_ctx* ctx, int M, int N, int K, int lda, int ldb) {
   (void)ctx;
   if (M < 1 || N < 1 || K < 1) return false;
-  if (M > 1024 || N > 1024) return false;  // weight-shaped outputs only
+  if (M > 4096 || N > 4096) return false;  // weight-shaped outputs only (the hot-column block has up to 4096 rows)
   if ((lda % 4) != 0 || (ldb % 4) != 0) return false;
   return encode_fn() != nullptr;
 }

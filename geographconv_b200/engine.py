@@ -153,7 +153,9 @@ def split_hot_columns(Xl, min_density, max_cols):
     nonzeros.  Those go to a dense N x Kh fp32 block that the tensor cores multiply (X_hot . W0[hot] forward,
     X_hot^T . dz backward); only the sparse tail pays the per-nonzero 1.2 KB gather.  A column is "hot" when its
     density (document frequency / rows) is at least ``min_density``; Kh is a multiple of 32, at most ``max_cols``.
-    Returns (hot_cols int32[Kh] ascending, X_hot float32[n, Kh], X_cold CSR) or (None, None, Xl).
+    Returns (hot_cols int32[Kh] ascending, X_hot CSR n x Kh with hot-local column ids, X_cold CSR) or
+    (None, None, Xl).  The hot block stays CSR on the host (a quarter of the dense bytes) and is expanded on the device
+    (gcnb_csr_to_dense_f32).
     """
     n, f = Xl.shape
     if n == 0 or Xl.nnz == 0 or max_cols < 32 or min_density <= 0:
@@ -170,8 +172,10 @@ def split_hot_columns(Xl, min_density, max_cols):
     m = hotmap[Xl.indices]
     is_hot = m >= 0
     rows = np.repeat(np.arange(n, dtype=np.int32), np.diff(Xl.indptr))
-    X_hot = np.zeros((n, kh), dtype=np.float32)
-    X_hot[rows[is_hot], m[is_hot]] = Xl.data[is_hot]
+    hot_counts = np.bincount(rows[is_hot], minlength=n)
+    hot_ptr = np.zeros(n + 1, dtype=np.int32)
+    np.cumsum(hot_counts, out=hot_ptr[1:])
+    X_hot = sp.csr_matrix((Xl.data[is_hot], m[is_hot], hot_ptr), shape=(n, kh))
     cold = ~is_hot
     counts = np.bincount(rows[cold], minlength=n)
     indptr = np.zeros(n + 1, dtype=np.int32)
@@ -208,8 +212,10 @@ class HostGraph:
             Xl, Al = X.tocsr(), A.tocsr()
         self.hot_cols, X_hot, Xl = split_hot_columns(Xl, hot_density, hot_max)
         self.kh = 0 if self.hot_cols is None else len(self.hot_cols)
-        self.X_hot = _pinned(X_hot.reshape(-1)) if self.kh else None
         self.hot_cols_p = _pinned(self.hot_cols) if self.kh else None
+        self.hot_ptr = _pinned(np.ascontiguousarray(X_hot.indptr, dtype=np.int32)) if self.kh else None
+        self.hot_col = _pinned(np.ascontiguousarray(X_hot.indices, dtype=np.int32)) if self.kh else None
+        self.hot_val = _pinned(np.ascontiguousarray(X_hot.data, dtype=np.float32)) if self.kh else None
         self.X = HostCsr(Xl, chunk)  # the cold columns only when a hot block exists
         self.A = HostCsr(Al, chunk)
         self.XT = self.AT = None
@@ -225,7 +231,7 @@ class HostGraph:
                 self.AT = HostCsr(ATl, chunk)
         self.nbytes = sum(c.nbytes for c in (self.X, self.XT, self.A, self.AT) if c is not None)
         if self.kh:
-            self.nbytes += self.X_hot.nbytes + self.hot_cols_p.nbytes
+            self.nbytes += self.hot_ptr.nbytes + self.hot_col.nbytes + self.hot_val.nbytes + self.hot_cols_p.nbytes
 
 
 class DeviceCsr:
@@ -294,8 +300,8 @@ class Engine:
         self.spmm_chunk = int(spmm_chunk)
         self.keep_logits = keep_logits
         # dense hot-column block of X (split_hot_columns): columns at least this dense, at most hot_max of them
-        self.hot_density = float(os.environ.get("GCNB_HOT_DENSITY", "0.05") if hot_density is None else hot_density)
-        self.hot_max = int(os.environ.get("GCNB_HOT_MAX", "1024") if hot_max is None else hot_max)
+        self.hot_density = float(os.environ.get("GCNB_HOT_DENSITY", "0.02") if hot_density is None else hot_density)
+        self.hot_max = int(os.environ.get("GCNB_HOT_MAX", "1536") if hot_max is None else hot_max)
         self.group = group
         self.world = torch.distributed.get_world_size(group) if group is not None else 1
         self.rank = torch.distributed.get_rank(group) if group is not None else 0
@@ -441,6 +447,9 @@ class Engine:
             if hg.kh:
                 self.X_hot = torch.empty((max(hg.n_loc, 1), hg.kh), dtype=torch.float32, device=self.dev)
                 self.hot_idx = torch.empty(hg.kh, dtype=torch.int32, device=self.dev)
+                self.hot_csr = (torch.empty(hg.hot_ptr.size, dtype=torch.int32, device=self.dev),
+                                torch.empty(max(hg.hot_col.size, 1), dtype=torch.int32, device=self.dev),
+                                torch.empty(max(hg.hot_val.size, 1), dtype=torch.float32, device=self.dev))
                 self._upload_hot(hg)
             self._alloc_buffers(need_backward)
             self._bound_key = key
@@ -471,7 +480,12 @@ class Engine:
 
     def _upload_hot(self, hg, ctx=None):
         ctx = self.ctx if ctx is None else ctx
-        ctx.call("gcnb_h2d", _ptr(self.X_hot), C.c_void_p(hg.X_hot.ctypes.data), hg.X_hot.nbytes)
+        # the hot block travels as CSR (hot-local column ids) and is expanded to the dense N x Kh operand on the device
+        for dst, src in zip(self.hot_csr, (hg.hot_ptr, hg.hot_col, hg.hot_val)):
+            if src.size:
+                ctx.call("gcnb_h2d", _ptr(dst), C.c_void_p(src.ctypes.data), src.nbytes)
+        ctx.call("gcnb_csr_to_dense_f32", _ptr(self.hot_csr[0]), _ptr(self.hot_csr[1]), _ptr(self.hot_csr[2]),
+                 hg.n_loc, hg.kh, _ptr(self.X_hot), hg.kh)
         ctx.call("gcnb_h2d", _ptr(self.hot_idx), C.c_void_p(hg.hot_cols_p.ctypes.data), hg.hot_cols_p.nbytes)
 
     def _wait_upload(self, *names):
@@ -821,8 +835,9 @@ class Engine:
         return loss, float(m[1]) / nt, float(m[2]) / nd, float(m[3]) / nd
 
     # ------------------------------------------------------------------ outputs
-    def gather_predictions(self, idx):
-        """argmax and probability rows of ``self.P`` at global indices ``idx`` (f_val outputs)."""
+    def gather_predictions(self, idx, want_probs=True):
+        """argmax and probability rows of ``self.P`` at global indices ``idx`` (f_val outputs).  ``want_probs=False``
+        returns (preds, device int64 tensor of the same predictions) and copies no probabilities to the host."""
         idx = np.ascontiguousarray(np.asarray(idx), dtype=np.int32)
         Cn = self.layout.output_size
         m = len(idx)
@@ -835,16 +850,17 @@ class Engine:
         self._keepalive = []
         d_idx = self.upload(idx)
         d_pred = torch.empty(max(m, 1), dtype=torch.int64, device=self.dev)
-        d_prob = torch.empty((max(m, 1), Cn), dtype=torch.float32, device=self.dev)
+        d_prob = torch.empty((max(m, 1), Cn), dtype=torch.float32, device=self.dev) if want_probs else None
         self.ctx.call("gcnb_gather_argmax_f32", _ptr(P), self.ldc, Cn, _ptr(d_idx), m, _ptr(d_pred), _ptr(d_prob))
         preds = np.empty(m, dtype=np.int64)
-        probs = np.empty((m, Cn), dtype=np.float32)
+        probs = np.empty((m, Cn), dtype=np.float32) if want_probs else None
         if m:
             self.ctx.call("gcnb_d2h", C.c_void_p(preds.ctypes.data), _ptr(d_pred), preds.nbytes)
-            self.ctx.call("gcnb_d2h", C.c_void_p(probs.ctypes.data), _ptr(d_prob), probs.nbytes)
+            if want_probs:
+                self.ctx.call("gcnb_d2h", C.c_void_p(probs.ctypes.data), _ptr(d_prob), probs.nbytes)
         self.ctx.sync()
         self._keepalive = []
-        return preds, probs
+        return (preds, probs) if want_probs else (preds, d_pred)
 
     def read_matrix(self, buf, rows, cols):
         """Device (rows_pad x ld) buffer -> host ndarray (rows x cols), gathered over ranks."""

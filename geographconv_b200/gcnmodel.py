@@ -226,6 +226,16 @@ class GraphConv():
         preds_test, prob_test = self.f_val(X, A, test_indices)
         return preds_test, prob_test
 
+    def predict_classes(self, X, A, test_indices):
+        """``predict`` without the probability rows: (int64[m] on the host, the same predictions as a device int64
+        tensor for ``geo.geo_eval(..., preds_device=...)``).  Nothing of size m x C crosses PCIe."""
+        eng = self._get_engine()
+        if not sp.issparse(X):
+            raise ValueError("Input for this layer must be sparse")
+        eng.bind(X, A, need_backward=False, force_upload=not self.cache_device_inputs)
+        eng.forward(train=False)
+        return eng.gather_predictions(test_indices, want_probs=False)
+
     def last_output(self):
         """N x C output of the most recent forward (the 5th output of the reference's f_train)."""
         eng = self._get_engine()

@@ -203,6 +203,12 @@ int gcnb_colsum_f32(gcnb_ctx* ctx, int32_t n_rows, int32_t k, const float* A, in
                     float* out, int32_t accumulate);
 size_t gcnb_colsum_workspace_bytes(int32_t n_rows, int32_t k);
 
+/* dense[n_rows x n_cols] (leading dimension ld) = the CSR matrix, zeros elsewhere.  The dense hot-column block of X
+ * travels host->device as CSR (a quarter of the bytes) and is expanded here.  Column ids must be < n_cols and
+ * unique inside a row. */
+int gcnb_csr_to_dense_f32(gcnb_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, const float* val,
+                          int32_t n_rows, int32_t n_cols, float* dense, int32_t ld);
+
 /* dst[i, :k] = src[idx[i], :k] for i < n_idx (rows of a weight matrix selected by column id: the dense
  * hot-column block of X multiplies W0[hot, :]).  scatter: dst[idx[i], :k] = src[i, :k]. */
 int gcnb_gather_rows_f32(gcnb_ctx* ctx, const float* src, int32_t ld_src, const int32_t* idx, int32_t n_idx,
@@ -224,6 +230,14 @@ int gcnb_xent_grad_f32(gcnb_ctx* ctx, const float* P, int32_t ldp, int32_t n_cla
  * f_val outputs: gcnmodel.py:393-394,411. */
 int gcnb_gather_argmax_f32(gcnb_ctx* ctx, const float* P, int32_t ldp, int32_t n_classes,
                            const int32_t* idx, int32_t n_idx, int64_t* preds, float* probs);
+
+/* dist[i] = haversine km between (lat_true[i], lon_true[i]) and the median location of the predicted class
+ * (class_lat[preds[i]], class_lon[preds[i]]): the loop of gcnmain.geo_eval (gcnmain.py:43-63) in float64.
+ * `preds` is the int64 device array gcnb_gather_argmax_f32 fills, so predictions never leave the GPU.  *bad_flag
+ * (device int32) is set when a prediction is outside [0, n_classes). */
+int gcnb_geo_distance_f64(gcnb_ctx* ctx, const int64_t* preds, int32_t n, const double* class_lat,
+                          const double* class_lon, int32_t n_classes, const double* lat_true,
+                          const double* lon_true, double radius_km, double* dist, int32_t* bad_flag);
 
 /* ---------------------------------------------------------------- optimiser ----------- */
 /* G += coef*(sign(W) + 2W); reg_sum[0] += sum(|W| + W^2)   (gcnmodel.py:383-387) */

@@ -191,7 +191,7 @@ def test_gemm_tcgen05_3xtf32(tB, M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K", [(300, 300, 5000), (129, 300, 20000), (300, 256, 777), (40, 24, 100), (512, 512, 4096),
-                                   (300, 300, 31), (7, 3, 5)])
+                                   (300, 300, 31), (7, 3, 5), (1536, 300, 3000), (2048, 129, 700)])
 def test_wgrad_tcgen05_split_k(M, N, K):
     """dW = x^T . V on tensor cores: MN-major operands, split over the node dimension, deterministic."""
     from geographconv_b200 import layers

@@ -2,6 +2,8 @@
 the derived 4-node known answer, SciPy's csr_matvecs, float64 finite differences, closed forms."""
 import ctypes
 
+import pytest
+
 import numpy as np
 import scipy.sparse as sp
 
@@ -162,3 +164,17 @@ def test_forward_shapes_and_softmax():
     assert len(f["gates"]) == 2 and f["gates"][0].shape == (30, 6)
     pr, pb = gcn_ref.predict(params, X, A, np.array([1, 5, 7]), hid, True)
     assert pr.dtype == np.int64 and pb.dtype == np.float32 and pb.shape == (3, 4)
+
+
+def test_geo_oracle_known_answer_and_statistics():
+    """haversine package's documented value (Lyon-Paris) pins the distance; geo_eval statistics follow gcnmain.py:57-63."""
+    from oracle import geo_ref
+    assert geo_ref.haversine((45.7597, 4.8422), (48.8567, 2.3508)) == pytest.approx(392.2172595594006, rel=1e-15)
+    assert geo_ref.haversine((10.0, 20.0), (10.0, 20.0)) == 0.0
+    lat = {"0": 40.0, "1": 30.0}
+    lon = {"0": -100.0, "1": -90.0}
+    loc = {"a": "40.0,-100.0", "b": "41.0,-100.0", "c": "30.0,-80.0"}
+    mean, median, acc, dist, t, p = geo_ref.geo_eval([0, 0, 1], [0, 0, 1], ["a", "b", "c"], lat, lon, loc)
+    assert dist[0] == 0.0 and dist[1] == pytest.approx(111.195, rel=1e-4) and dist[2] > 161
+    assert acc == pytest.approx(100 * 2 / 3.0) and median == dist[1] and mean == pytest.approx(sum(dist) / 3)
+    assert t == [[40.0, -100.0], [41.0, -100.0], [30.0, -80.0]] and p == [[40.0, -100.0], [40.0, -100.0], [30.0, -90.0]]
