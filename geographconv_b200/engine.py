@@ -300,8 +300,9 @@ class Engine:
         self.spmm_chunk = int(spmm_chunk)
         self.keep_logits = keep_logits
         # dense hot-column block of X (split_hot_columns): columns at least this dense, at most hot_max of them
-        self.hot_density = float(os.environ.get("GCNB_HOT_DENSITY", "0.02") if hot_density is None else hot_density)
-        self.hot_max = int(os.environ.get("GCNB_HOT_MAX", "1536") if hot_max is None else hot_max)
+        # (measured on C3: 1024 columns at >= 5% density; 1536 columns save 1.1 ms of SpMM and cost 2.1 ms of GEMM)
+        self.hot_density = float(os.environ.get("GCNB_HOT_DENSITY", "0.05") if hot_density is None else hot_density)
+        self.hot_max = int(os.environ.get("GCNB_HOT_MAX", "1024") if hot_max is None else hot_max)
         self.group = group
         self.world = torch.distributed.get_world_size(group) if group is not None else 1
         self.rank = torch.distributed.get_rank(group) if group is not None else 0
