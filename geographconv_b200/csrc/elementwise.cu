@@ -108,12 +108,25 @@ __global__ void __launch_bounds__(kThreads) colsum_stage1_kernel(int n_rows, int
     __syncthreads();
   }
 }
-__global__ void colsum_stage2_kernel(int nblocks, int k, size_t stride, const float* partial, float* out, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= k) return;
+// stage 2: out[c] (+)= sum over blocks of partial[b * stride + c].  A CTA owns 32 consecutive columns: warp w adds
+// blocks w, w+8, ... (coalesced 128-byte reads), then the 8 warp sums are added in warp order: a fixed order, so the
+// result is deterministic.
+__global__ void __launch_bounds__(kThreads) colsum_stage2_kernel(int nblocks, int k, size_t stride, const float* partial,
+                                                                 float* out, int accumulate) {
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * stride + c];
-  out[c] = accumulate ? out[c] + s : s;
+  if (c < k)
+    for (int b = warp; b < nblocks; b += 8) s += partial[(size_t)b * stride + c];
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && c < k) {
+    float t = red[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) t += red[w][lane];
+    out[c] = accumulate ? out[c] + t : t;
+  }
 }
 
 // block-level column sum of per-thread float4 partials (8 warps x 32 lanes): warp 0 adds the 8 warps in order
@@ -446,9 +459,9 @@ extern "C" int gcnb_highway_bwd_bias_f32(gcnb_ctx* ctx, int32_t n_rows, int32_t 
   else GCNB_LAUNCH_HWB(4);
 #undef GCNB_LAUNCH_HWB
   GCNB_LAUNCHED(ctx);
-  colsum_stage2_kernel<<<cdiv(hd, 128), 128, 0, ctx->stream>>>(blocks, hd, (size_t)nf4 * 8, partial, dbh, 0);
+  colsum_stage2_kernel<<<cdiv(hd, 32), kThreads, 0, ctx->stream>>>(blocks, hd, (size_t)nf4 * 8, partial, dbh, 0);
   GCNB_LAUNCHED(ctx);
-  colsum_stage2_kernel<<<cdiv(hd, 128), 128, 0, ctx->stream>>>(blocks, hd, (size_t)nf4 * 8, partial + (size_t)nf4 * 4, dbt, 0);
+  colsum_stage2_kernel<<<cdiv(hd, 32), kThreads, 0, ctx->stream>>>(blocks, hd, (size_t)nf4 * 8, partial + (size_t)nf4 * 4, dbt, 0);
   GCNB_LAUNCHED(ctx);
   return GCNB_OK;
 }
@@ -485,7 +498,7 @@ extern "C" int gcnb_act_bwd_bias_f32(gcnb_ctx* ctx, int32_t n_rows, int32_t k, i
   else GCNB_LAUNCH_AB(4);
 #undef GCNB_LAUNCH_AB
   GCNB_LAUNCHED(ctx);
-  colsum_stage2_kernel<<<cdiv(k, 128), 128, 0, ctx->stream>>>(blocks, k, (size_t)nf4 * 4, partial, db, 0);
+  colsum_stage2_kernel<<<cdiv(k, 32), kThreads, 0, ctx->stream>>>(blocks, k, (size_t)nf4 * 4, partial, db, 0);
   GCNB_LAUNCHED(ctx);
   return GCNB_OK;
 }
@@ -528,7 +541,7 @@ extern "C" int gcnb_colsum_f32(gcnb_ctx* ctx, int32_t n_rows, int32_t k, const f
   float* partial = reinterpret_cast<float*>(ctx->ws);
   colsum_stage1_kernel<<<blocks, kThreads, 0, ctx->stream>>>(n_rows, nf4, A, lda, partial);
   GCNB_LAUNCHED(ctx);
-  colsum_stage2_kernel<<<cdiv(k, 128), 128, 0, ctx->stream>>>(blocks, k, (size_t)nf4 * 4, partial, out, accumulate);
+  colsum_stage2_kernel<<<cdiv(k, 32), kThreads, 0, ctx->stream>>>(blocks, k, (size_t)nf4 * 4, partial, out, accumulate);
   GCNB_LAUNCHED(ctx);
   return GCNB_OK;
 }

@@ -59,6 +59,7 @@ struct SpmmParams {
   int pcol0;       // first column of this pass inside a partial slot (0 unless the slots span all of K: panel engine)
   int k4;          // K rounded up to 4 (panel engine: the panels tile [0, k4))
   int evict_last;  // panel engine: gathers carry an L2 evict_last hint
+  int col_base;    // panel engine: first column of panel 0 of this launch
 };
 
 constexpr int kWarpsPerCta = 8;
@@ -426,7 +427,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GL * R <= 8 ? 4 : 2) spmm_p
   constexpr int NB = GL * R;
   const int lane = threadIdx.x & 31;
   const int g = lane / GL, gl = lane % GL;
-  const int col0 = (int)blockIdx.y * (GL * 4);
+  const int col0 = p.col_base + (int)blockIdx.y * (GL * 4);
   const int item = (blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)) * G + g;
   const bool valid = item < p.n_items;
   int4 it = make_int4(0, 0, 0, -1);
@@ -644,25 +645,35 @@ int launch_panels(gcnb_ctx* ctx, const SpmmParams& p0, int n_rows, int K4, int u
   p.ldp = K4;
   p.evict_last = ctx->spmm_panel_policy != 0;
   if (p.n_items > 0) {
-    const int GL = PW / 4, G = 32 / GL;
-    const dim3 grid(cdiv(p.n_items, kWarpsPerCta * G), cdiv(K4, PW));
     const int threads = kWarpsPerCta * 32;
-#define GCNB_PANEL(GLV, RV)                                                                   \
-  do {                                                                                        \
-    if (p.evict_last) spmm_panel_kernel<GLV, RV, true><<<grid, threads, 0, ctx->stream>>>(p); \
-    else spmm_panel_kernel<GLV, RV, false><<<grid, threads, 0, ctx->stream>>>(p);             \
+#define GCNB_PANEL(GLV, RV, NPANELS)                                                                      \
+  do {                                                                                                    \
+    const dim3 grid(cdiv(p.n_items, kWarpsPerCta * (32 / GLV)), NPANELS);                                 \
+    if (p.evict_last) spmm_panel_kernel<GLV, RV, true><<<grid, threads, 0, ctx->stream>>>(p);             \
+    else spmm_panel_kernel<GLV, RV, false><<<grid, threads, 0, ctx->stream>>>(p);                         \
+    GCNB_LAUNCHED(ctx);                                                                                   \
   } while (0)
-    if (GL == 4) {
-      if (unroll >= 16) GCNB_PANEL(4, 4);
-      else GCNB_PANEL(4, 2);
-    } else if (GL == 8) {
-      if (unroll >= 16) GCNB_PANEL(8, 2);
-      else GCNB_PANEL(8, 1);
+    if (PW == 32) {
+      // full 32-column panels, then a remainder of at most 16 columns on 4-lane groups (8 items per warp): K = 300
+      // is 9 panels + 12 columns, and a tenth 8-lane pass would spend a full pass on 12 useful columns
+      const int full = K4 / 32, rem = K4 - 32 * full;
+      const int n32 = rem > 16 ? full + 1 : full;
+      if (n32 > 0) {
+        if (unroll >= 16) GCNB_PANEL(8, 2, n32);
+        else GCNB_PANEL(8, 1, n32);
+      }
+      if (rem > 0 && rem <= 16) {
+        p.col_base = 32 * full;
+        GCNB_PANEL(4, 2, 1);
+        p.col_base = 0;
+      }
+    } else if (PW == 16) {
+      if (unroll >= 16) GCNB_PANEL(4, 4, cdiv(K4, 16));
+      else GCNB_PANEL(4, 2, cdiv(K4, 16));
     } else {
-      GCNB_PANEL(16, 1);
+      GCNB_PANEL(16, 1, cdiv(K4, 64));
     }
 #undef GCNB_PANEL
-    GCNB_LAUNCHED(ctx);
   }
   for (int pass = 0; pass < 2; ++pass) {  // 0: long-row fix-up, 1: row softmax
     if (pass == 0 && p.n_long == 0) continue;
