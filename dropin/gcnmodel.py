@@ -12,5 +12,7 @@ if _ROOT not in sys.path:
     sys.path.insert(0, _ROOT)
 
 from geographconv_b200.gcnmodel import (  # noqa: E402,F401
-    GraphConv, SparseInputDenseLayer, SparseConvolutionDenseLayer, SparseConvolutionLayer,
-    ConvolutionDenseLayer2, ConvolutionDenseLayer3, initial_parameters)
+    GraphConv, SparseInputDenseLayer, SparseInputDropoutLayer, SparseConvolutionDenseLayer, SparseConvolutionLayer,
+    SparseConvolutionDenseLayer2, ConvolutionDenseLayer, ConvolutionDenseLayer2, ConvolutionDenseLayer3,
+    ConvolutionDenseLayer_zero, ConvolutionLayer, DenseLayer2, MultiplicativeGatingLayer, highway_dense, residual_dense,
+    np_softmax, iterate_minibatches, initial_parameters)

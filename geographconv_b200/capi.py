@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgcnb200.so")
 
 OK, E_INVALID, E_CUDA, E_WORKSPACE, E_UNSUPPORTED = 0, -1, -2, -3, -4
-ACT = {"linear": 0, "tanh": 1, "relu": 2, "rectify": 2, "sigmoid": 3}
+ACT = {"linear": 0, "tanh": 1, "relu": 2, "rectify": 2, "sigmoid": 3, "selu": 4, None: 0}
 TAGS = ["spmm_a", "spmm_x", "spmm_xt", "gemm", "elementwise", "loss", "adam", "copy", "spmm_a_narrow"]
 TAG_SPMM_A, TAG_SPMM_X, TAG_SPMM_XT, TAG_SPMM_A_NARROW = 0, 1, 2, 8
 
@@ -73,6 +73,7 @@ SIGNATURES = {
     "gcnb_highway_fwd_f32": (C.c_int, [_ctxp, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _i32,
                                        _vp, _i32, _vp, _i32, _vp, _i32]),
     "gcnb_highway_workspace_bytes": (_sz, [_i32, _i32]),
+    "gcnb_highway_mix_f32": (C.c_int, [_ctxp, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32]),
     "gcnb_highway_bwd_f32": (C.c_int, [_ctxp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "gcnb_act_bwd_f32": (C.c_int, [_ctxp, _i32, _i32, _i32, _vp, _vp, _i32, _f32, _u64, _i64, _vp]),
     "gcnb_highway_bwd_bias_f32": (C.c_int, [_ctxp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),

@@ -222,7 +222,7 @@ extern "C" int gcnb_gemm_f32(gcnb_ctx* ctx, int32_t transA, int32_t transB, int3
   if (ctx->gemm_tc && transA && !transB && !bias && act == GCNB_ACT_LINEAR &&
       gcnb_wgrad_tc_supported(ctx, M, N, K, lda, ldb))
     return gcnb_wgrad_tc(ctx, M, N, K, A, lda, B, ldb, C, ldc, accumulate);
-  if (ctx->gemm_tc && gcnb_gemm_tc_supported(ctx, transA, transB, M, N, K, lda, ldb, ldc, accumulate))
+  if (ctx->gemm_tc && act <= GCNB_ACT_SIGMOID && gcnb_gemm_tc_supported(ctx, transA, transB, M, N, K, lda, ldb, ldc, accumulate))
     return gcnb_gemm_tc(ctx, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, act, accumulate);
   return gcnb_gemm_simt(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, accumulate, bias, act);
 }
@@ -245,6 +245,19 @@ extern "C" int gcnb_gemm_pair_f32(gcnb_ctx* ctx, int32_t transB, int32_t M, int3
   return gcnb_gemm_simt(ctx, 0, transB, M, N, K, A2, lda2, B2, ldb2, C, ldc, 1, nullptr, GCNB_ACT_LINEAR);
 }
 
+extern "C" int gcnb_highway_mix_f32(gcnb_ctx* ctx, int32_t n_rows, int32_t hd, const float* H, int32_t ldh, const float* T,
+                                    int32_t ldt, const float* X, int32_t ldx, float* Y, int32_t ldy) {
+  if (!ctx) return GCNB_E_INVALID;
+  GCNB_REQUIRE(ctx, H && T && X && Y, "null pointer");
+  const int hd4 = ((hd + 3) / 4) * 4;
+  GCNB_REQUIRE(ctx, ldh % 4 == 0 && ldt % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldh >= hd4 && ldt >= hd4 &&
+                        ldx >= hd4 && ldy >= hd4,
+               "leading dimensions: multiple of 4, >= hd rounded to 4");
+  if (n_rows == 0) return GCNB_OK;
+  ProfScope scope(ctx, GCNB_TAG_ELEM);
+  return gcnb_highway_mix(ctx, n_rows, hd, H, ldh, T, ldt, X, ldx, Y, ldy);
+}
+
 extern "C" size_t gcnb_highway_workspace_bytes(int32_t n_rows, int32_t hd) {
   // CUDA-core path: H and T scratch when the caller does not keep them; tcgen05 path: split weights
   const size_t ld = ((size_t)hd + 31) / 32 * 32;
@@ -264,7 +277,7 @@ extern "C" int gcnb_highway_fwd_f32(gcnb_ctx* ctx, int32_t n_rows, int32_t hd, c
                "lds/ldx/ldy: multiple of 4, >= hd rounded to 4");
   GCNB_REQUIRE(ctx, (!H || (ldh % 4 == 0 && ldh >= hd4)) && (!T || (ldt % 4 == 0 && ldt >= hd4)), "ldh/ldt");
   if (n_rows == 0) return GCNB_OK;
-  if (ctx->gemm_tc && gcnb_highway_tc_supported(ctx, n_rows, hd, lds, ldx, ldwh, ldwt)) {
+  if (ctx->gemm_tc && act <= GCNB_ACT_SIGMOID && gcnb_highway_tc_supported(ctx, n_rows, hd, lds, ldx, ldwh, ldwt)) {
     ProfScope scope(ctx, GCNB_TAG_GEMM);
     return gcnb_highway_tc(ctx, n_rows, hd, S, lds, X, ldx, Wh, ldwh, bh, Wt, ldwt, bt, act, Y, ldy, H, ldh, T, ldt);
   }

@@ -113,6 +113,7 @@ __device__ __forceinline__ float act_apply(int act, float z) {
     case GCNB_ACT_TANH: return tanhf(z);
     case GCNB_ACT_RELU: return fmaxf(z, 0.f);
     case GCNB_ACT_SIGMOID: return 1.f / (1.f + expf(-z));
+    case GCNB_ACT_SELU: return 1.0507009873554805f * (z > 0.f ? z : 1.6732632423543772f * expm1f(z));
     default: return z;
   }
 }
@@ -122,6 +123,7 @@ __device__ __forceinline__ float act_grad_from_out(int act, float y) {
     case GCNB_ACT_TANH: return 1.f - y * y;
     case GCNB_ACT_RELU: return y > 0.f ? 1.f : 0.f;
     case GCNB_ACT_SIGMOID: return y * (1.f - y);
+    case GCNB_ACT_SELU: return y > 0.f ? 1.0507009873554805f : y + 1.0507009873554805f * 1.6732632423543772f;
     default: return 1.f;
   }
 }

@@ -298,14 +298,48 @@ class SparseInputDenseLayer(_SingleLayer):
         return sparse_dense(input, self.W, self.b, self.nonlinearity, device=self._device)
 
 
+def _take_rows(out, target_indices, use=True):
+    """``activation[target_indices, :]`` (gcnmodel.py:110,199,218): row gather of the host result."""
+    if use and target_indices is not None and len(target_indices):
+        return out[np.asarray(target_indices)]
+    return out
+
+
+class SparseInputDropoutLayer:
+    """Dropout on a sparse input (gcnmodel.py:44-70): stored entries are kept with probability 1-p and rescaled by
+    1/(1-p); ``deterministic`` or p == 0 returns the input.  The keep mask is drawn on the device with the engine's
+    Philox stream (one draw per stored entry), not Theano's MRG stream."""
+
+    def __init__(self, p=0.5, rescale=True, device=None):
+        self.p, self.rescale, self._device = float(p), bool(rescale), device
+
+    def get_output_for(self, input, deterministic=False, seed=0, **kwargs):
+        if not sp.issparse(input):
+            raise ValueError("Input for this layer must be sparse")
+        if deterministic or self.p == 0:
+            return input
+        from .layers import dropout_keep_mask
+        X = sp.csr_matrix(input, dtype=np.float32, copy=True)
+        keep = dropout_keep_mask(1, X.nnz, self.p, seed, device=self._device)[0]
+        scale = np.float32(1.0 / (1.0 - self.p)) if self.rescale else np.float32(1.0)
+        X.data = X.data * scale * keep.astype(np.float32)
+        return X
+
+
 class SparseConvolutionDenseLayer(_SingleLayer):
-    """act(A.(X.W) + b) for sparse X and sparse A (gcnmodel.py:72-92)."""
+    """act(A.(X.W) + b) for sparse X and sparse A (gcnmodel.py:72-92); ``A`` is a constructor argument there and may be
+    given at either place here.  Without any A the convolution is skipped (gcnmodel.py:242)."""
+
+    def __init__(self, num_units, nonlinearity='tanh', device=None, A=None):
+        super().__init__(num_units, nonlinearity, device)
+        self.A = A
 
     def get_output_for(self, input, A=None, **kwargs):
         if not sp.issparse(input):
             raise ValueError("Input for this layer must be sparse")
         from .layers import sparse_dense, graph_conv_dense
         self._init(input.shape[1])
+        A = self.A if A is None else A
         if A is None:
             return sparse_dense(input, self.W, self.b, self.nonlinearity, device=self._device)
         return graph_conv_dense(A, sparse_dense(input, self.W, None, 'linear', device=self._device), None, self.b,
@@ -313,6 +347,14 @@ class SparseConvolutionDenseLayer(_SingleLayer):
 
 
 SparseConvolutionLayer = SparseConvolutionDenseLayer  # the name BASELINE.json's north_star uses
+
+
+class SparseConvolutionDenseLayer2(SparseConvolutionDenseLayer):
+    """The call-time-A variant (gcnmodel.py:224-249): ``get_output_for(input, A=...)``; falsy A skips the convolution."""
+
+    def __init__(self, num_units, nonlinearity='tanh', device=None, use_target_indices=False):
+        super().__init__(num_units, nonlinearity, device)
+        self.use_target_indices = use_target_indices
 
 
 class ConvolutionDenseLayer2(_SingleLayer):
@@ -330,3 +372,111 @@ class ConvolutionDenseLayer3(ConvolutionDenseLayer2):
 
     def __init__(self, num_units, nonlinearity='softmax', device=None):
         super().__init__(num_units, nonlinearity, device)
+
+
+class ConvolutionDenseLayer_zero(ConvolutionDenseLayer2):
+    """act(A.(x.W) + b) with A a constructor argument (gcnmodel.py:159-179)."""
+
+    def __init__(self, num_units, nonlinearity='tanh', device=None, A=None):
+        super().__init__(num_units, nonlinearity, device)
+        self.A = A
+
+    def get_output_for(self, input, **kwargs):
+        return super().get_output_for(input, A=self.A)
+
+
+class ConvolutionDenseLayer(ConvolutionDenseLayer_zero):
+    """act((A.(x.W) + b)[target_indices, :]) (gcnmodel.py:94-112).  The activation is element-wise, so gathering the
+    rows of the activated matrix is the same thing."""
+
+    def get_output_for(self, input, target_indices=None, **kwargs):
+        return _take_rows(super().get_output_for(input), target_indices)
+
+
+class ConvolutionLayer:
+    """act((A.x)[target_indices, :]): a graph convolution without weights (gcnmodel.py:181-201)."""
+
+    def __init__(self, use_target_indices=False, A=None, nonlinearity='linear', device=None):
+        self.use_target_indices, self.A, self.nonlinearity, self._device = use_target_indices, A, nonlinearity, device
+
+    def get_output_for(self, input, target_indices=None, **kwargs):
+        from .layers import spmm
+        out = spmm(self.A, np.asarray(input, dtype=np.float32), act=self.nonlinearity or 'linear', device=self._device)
+        return _take_rows(out, target_indices, self.use_target_indices)
+
+
+class DenseLayer2(_SingleLayer):
+    """act((x.W + b)[target_indices, :]) (gcnmodel.py:203-221)."""
+
+    def __init__(self, num_units, nonlinearity='tanh', device=None, use_target_indices=False):
+        super().__init__(num_units, nonlinearity, device)
+        self.use_target_indices = use_target_indices
+
+    def get_output_for(self, input, target_indices=None, **kwargs):
+        from .layers import gemm
+        self._init(np.shape(input)[1])
+        out = gemm(np.asarray(input, dtype=np.float32), self.W, bias=self.b, act=self.nonlinearity or 'linear',
+                   device=self._device)
+        return _take_rows(out, target_indices, self.use_target_indices)
+
+
+class MultiplicativeGatingLayer:
+    """y = t*h1 + (1-t)*h2 for inputs [t, h1, h2] of equal shape (gcnmodel.py:252-266)."""
+
+    def __init__(self, device=None):
+        self._device = device
+
+    def get_output_for(self, inputs, **kwargs):
+        t, h1, h2 = (np.asarray(v, dtype=np.float32) for v in inputs)
+        assert t.shape == h1.shape == h2.shape  # gcnmodel.py:260
+        from .layers import gate_mix
+        return gate_mix(t, h1, h2, device=self._device)
+
+
+def highway_dense(x, A=None, gconv=False, Wh=None, bh=None, Wt=None, bt=None, nonlinearity='sigmoid', device=None):
+    """Highway layer on host arrays (gcnmodel.py:268-288): h = act(conv(x.Wh) + bh) with conv = A. when ``gconv``,
+    t = sigmoid(x.Wt + bt), returns (t*h + (1-t)*x, t).  Default initialisers like the reference: Wh, Wt Glorot
+    uniform, bh = 0, bt = -4 (gcnmodel.py:271-274); Wh is drawn before Wt.  Note the reference's default activation of
+    the h branch here is the sigmoid; ``GraphConv`` passes its own (gcnmodel.py:361)."""
+    from .layers import highway, spmm
+    x = np.asarray(x, dtype=np.float32)
+    n_in = x.shape[1]
+    Wh = _glorot_uniform((n_in, n_in)) if Wh is None else Wh
+    Wt = _glorot_uniform((n_in, n_in)) if Wt is None else Wt
+    bh = np.zeros(n_in, "float32") if bh is None else bh
+    bt = np.full(n_in, -4.0, "float32") if bt is None else bt
+    S = spmm(A, x, device=device) if gconv else x
+    y, _, t = highway(S, x, Wh, bh, Wt, bt, act=nonlinearity, device=device)
+    return y, t
+
+
+def residual_dense(x, A, W=None, b=None, nonlinearity='selu', device=None):
+    """nonlinearity(A.(x.W) + b + x) (gcnmodel.py:290-294): one GEMM, then one SpMM whose epilogue adds the residual
+    and applies the SELU."""
+    from .layers import gemm, spmm
+    x = np.asarray(x, dtype=np.float32)
+    n_in = x.shape[1]
+    W = _glorot_uniform((n_in, n_in)) if W is None else W
+    b = np.zeros(n_in, "float32") if b is None else b
+    q = gemm(x, W, device=device)
+    return spmm(A, q, bias=b, act=nonlinearity or 'linear', accumulate_into=x, accumulate_mode=2, device=device)
+
+
+def np_softmax(x):
+    """gcnmodel.py:298-301 (softmax over ALL entries of x, as the reference writes it)."""
+    e_x = np.exp(x - np.max(x))
+    return e_x / e_x.sum()
+
+
+def iterate_minibatches(inputs, targets, batchsize, shuffle=False):
+    """gcnmodel.py:303-313."""
+    assert inputs.shape[0] == targets.shape[0]
+    if shuffle:
+        indices = np.arange(inputs.shape[0])
+        np.random.shuffle(indices)
+    for start_idx in range(0, inputs.shape[0] - batchsize + 1, batchsize):
+        if shuffle:
+            excerpt = indices[start_idx:start_idx + batchsize]
+        else:
+            excerpt = slice(start_idx, start_idx + batchsize)
+        yield inputs[excerpt], targets[excerpt]

@@ -217,3 +217,32 @@ def graph_conv_dense(A, x, W, b, act="tanh", device=None):
     if act == "softmax":
         return spmm(A, q, bias=b, softmax=True, device=device)
     return spmm(A, q, bias=b, act=act, device=device)
+
+
+def gate_mix(t, h1, h2, device=None):
+    """t*h1 + (1-t)*h2 (MultiplicativeGatingLayer, gcnmodel.py:266) on the device."""
+    d = get_dev(device)
+    t = np.asarray(t, dtype=np.float32)
+    n, k = t.shape
+    dT, ld = d.dense(t)
+    dH, _ = d.dense(h1)
+    dX, _ = d.dense(h2)
+    dY = torch.zeros(max(n, 1) * ld, dtype=torch.float32, device=d.dev)
+    p = lambda x: C.c_void_p(x.data_ptr())
+    d.fence()
+    d.ctx.call("gcnb_highway_mix_f32", n, k, p(dH), ld, p(dT), ld, p(dX), ld, p(dY), ld)
+    return d.download(dY, n, ld, k)
+
+
+def dropout_keep_mask(n_rows, k, p, seed, row0=0, device=None):
+    """uint8 keep mask (n_rows x k) of the engine's Philox dropout stream (gcnb_dropout_mask_u8)."""
+    d = get_dev(device)
+    m = torch.empty(max(n_rows * k, 1), dtype=torch.uint8, device=d.dev)
+    d.fence()
+    d.ctx.call("gcnb_dropout_mask_u8", int(n_rows), int(k), float(p), int(seed) & (2**64 - 1), int(row0),
+               C.c_void_p(m.data_ptr()))
+    host = np.empty((n_rows, k), dtype=np.uint8)
+    if host.size:
+        d.ctx.call("gcnb_d2h", C.c_void_p(host.ctypes.data), C.c_void_p(m.data_ptr()), host.nbytes)
+    d.ctx.sync()
+    return host

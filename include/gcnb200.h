@@ -41,8 +41,9 @@ enum gcnb_status {
 };
 
 /* lasagne.nonlinearities used by gcnmodel.py: tanh (:347, live), rectify (:345, commented
- * out), sigmoid (:286 gate), linear (:188). */
-enum gcnb_act { GCNB_ACT_LINEAR = 0, GCNB_ACT_TANH = 1, GCNB_ACT_RELU = 2, GCNB_ACT_SIGMOID = 3 };
+ * out), sigmoid (:286 gate), linear (:188), selu (:290 residual_dense; element-wise epilogues of the SpMM
+ * and the CUDA-core GEMM only -- the tcgen05 GEMM declines it). */
+enum gcnb_act { GCNB_ACT_LINEAR = 0, GCNB_ACT_TANH = 1, GCNB_ACT_RELU = 2, GCNB_ACT_SIGMOID = 3, GCNB_ACT_SELU = 4 };
 
 /* profiling classes: the step-time split SURVEY.md 8d asks for */
 enum gcnb_tag {
@@ -175,6 +176,10 @@ int gcnb_highway_fwd_f32(gcnb_ctx* ctx, int32_t n_rows, int32_t hd, const float*
                          int32_t act, float* Y, int32_t ldy, float* H, int32_t ldh, float* T,
                          int32_t ldt);
 size_t gcnb_highway_workspace_bytes(int32_t n_rows, int32_t hd);
+
+/* Y = T*H + (1-T)*X   (MultiplicativeGatingLayer.get_output_for, gcnmodel.py:266), element-wise */
+int gcnb_highway_mix_f32(gcnb_ctx* ctx, int32_t n_rows, int32_t hd, const float* H, int32_t ldh, const float* T,
+                         int32_t ldt, const float* X, int32_t ldx, float* Y, int32_t ldy);
 
 /* backward of the gate mix: dHpre = dY*T*act'(H), dTpre = dY*(H-X)*T*(1-T), dX = dY*(1-T) */
 int gcnb_highway_bwd_f32(gcnb_ctx* ctx, int32_t n_rows, int32_t hd, int32_t ld, const float* dY,
