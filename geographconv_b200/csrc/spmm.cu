@@ -375,6 +375,14 @@ __device__ __forceinline__ uint64_t policy_evict_last() {
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
+// same with L1 allocation (gathered operands with reuse inside an SM: the frequent terms of X.W0)
+__device__ __forceinline__ float4 ld_gather_hint_l1_f4(const float4* p, uint64_t pol) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p), "l"(pol));
+  return r;
+}
 __device__ __forceinline__ float4 ld_gather_hint_f4(const float4* p, uint64_t pol) {
   float4 r;
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
@@ -421,7 +429,7 @@ __device__ __forceinline__ void panel_epilogue(const SpmmParams& p, int row, int
 // GL lanes per row item (panel = 4*GL floats), R (column, value) pairs per lane and batch: GL*R gathers in flight.
 // KEEP: gathers carry an L2 evict_last hint.  Batches in which every item of the warp still has GL*R nonzeros run
 // without predicates (plans sorted by item length make that the common case); the rest take the predicated tail.
-template <int GL, int R, bool KEEP>
+template <int GL, int R, int KEEP>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, GL * R <= 8 ? 4 : 2) spmm_panel_kernel(const SpmmParams p) {
   constexpr int G = 32 / GL;
   constexpr int NB = GL * R;
@@ -447,7 +455,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, GL * R <= 8 ? 4 : 2) spmm_p
 
   auto gather = [&](int cj) -> float4 {
     const float4* src = reinterpret_cast<const float4*>(Bs + (uint64_t)(uint32_t)cj * row_bytes);
-    return KEEP ? ld_gather_hint_f4(src, keep) : ld_gather_f4(src);
+    return KEEP == 2 ? ld_gather_hint_l1_f4(src, keep) : KEEP == 1 ? ld_gather_hint_f4(src, keep) : ld_gather_f4(src);
   };
 
   int base = 0;
@@ -643,14 +651,15 @@ int launch_panels(gcnb_ctx* ctx, const SpmmParams& p0, int n_rows, int K4, int u
   p.k4 = K4;
   p.nf4 = K4 / 4;
   p.ldp = K4;
-  p.evict_last = ctx->spmm_panel_policy != 0;
+  p.evict_last = ctx->spmm_panel_policy;
   if (p.n_items > 0) {
     const int threads = kWarpsPerCta * 32;
 #define GCNB_PANEL(GLV, RV, NPANELS)                                                                      \
   do {                                                                                                    \
     const dim3 grid(cdiv(p.n_items, kWarpsPerCta * (32 / GLV)), NPANELS);                                 \
-    if (p.evict_last) spmm_panel_kernel<GLV, RV, true><<<grid, threads, 0, ctx->stream>>>(p);             \
-    else spmm_panel_kernel<GLV, RV, false><<<grid, threads, 0, ctx->stream>>>(p);                         \
+    if (p.evict_last == 2) spmm_panel_kernel<GLV, RV, 2><<<grid, threads, 0, ctx->stream>>>(p);           \
+    else if (p.evict_last) spmm_panel_kernel<GLV, RV, 1><<<grid, threads, 0, ctx->stream>>>(p);           \
+    else spmm_panel_kernel<GLV, RV, 0><<<grid, threads, 0, ctx->stream>>>(p);                             \
     GCNB_LAUNCHED(ctx);                                                                                   \
   } while (0)
     if (PW == 32) {
