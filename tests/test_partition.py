@@ -117,3 +117,30 @@ def test_row_partitioned_exchange_world2_gloo():
         np.testing.assert_allclose(full, ref["probs"], rtol=1e-4, atol=1e-6)
         assert cnt == len(tr)
         assert abs(loss - want_loss) < 1e-4
+
+
+def test_hot_column_split_reassembles_x():
+    """split_hot_columns: hot CSR (hot-local ids) + cold CSR partition X's nonzeros; hot ids ascending; nothing when the
+    matrix has no dense columns."""
+    import scipy.sparse as sp
+    from geographconv_b200.engine import split_hot_columns, panel_col_blocks
+    rng = np.random.RandomState(3)
+    n, f = 400, 600
+    dense_cols = rng.choice(f, size=100, replace=False)
+    M = sp.random(n, f, density=0.01, random_state=rng, format="lil", dtype=np.float32)
+    for c in dense_cols:
+        rows = rng.choice(n, size=n // 3, replace=False)
+        M[rows, c] = rng.rand(len(rows)).astype(np.float32) + 0.1
+    X = M.tocsr().astype(np.float32)
+    X.sort_indices()
+    hot_cols, X_hot, X_cold = split_hot_columns(X, 0.2, 96)
+    assert len(hot_cols) == 96 and (np.diff(hot_cols) > 0).all() and set(hot_cols) <= set(dense_cols.tolist())
+    assert X_hot.shape == (n, 96) and X_cold.shape == X.shape and X_hot.nnz + X_cold.nnz == X.nnz
+    back = X_cold.toarray()
+    back[:, hot_cols] += X_hot.toarray()
+    np.testing.assert_array_equal(back, X.toarray())
+    assert not X_cold[:, hot_cols].nnz
+    assert split_hot_columns(X, 0.9, 96)[0] is None          # no column that dense
+    assert split_hot_columns(X, 0.2, 16)[0] is None          # fewer than 64 hot columns allowed: not worth a GEMM
+    # panel working-set rule: 16 MB of 128-byte panel lines per block, at most 8 blocks
+    assert panel_col_blocks(62_500) == 1 and panel_col_blocks(500_000) == 4 and panel_col_blocks(10_000_000) == 8
