@@ -192,7 +192,7 @@ class HostGraph:
     memory across epochs, gcnmain.py:172-179) and cached by the engine."""
 
     def __init__(self, X, A, world, rank, chunk, need_backward, assume_symmetric=None, hot_density=0.0,
-                 hot_max=0):
+                 hot_max=0, xt_blocks=0):
         n = X.shape[0]
         self.n = n
         self.n_pad, blocks = row_blocks(n, world)
@@ -222,7 +222,7 @@ class HostGraph:
         self.symmetric = True
         if need_backward:
             XTl = transpose_csr(Xl)
-            self.XT = HostCsr(XTl, chunk, col_blocks=panel_col_blocks(XTl.shape[1]))
+            self.XT = HostCsr(XTl, chunk, col_blocks=xt_blocks if xt_blocks > 0 else panel_col_blocks(XTl.shape[1]))
             self.symmetric = bool(is_symmetric(A) if assume_symmetric is None else assume_symmetric)
             if not self.symmetric:
                 # A^T.G for a row block needs rows r0:r1 of A^T
@@ -253,7 +253,9 @@ class DeviceCsr:
         s.items, s.n_items = self.t_items.data_ptr(), host.n_items
         s.long_rows = self.t_long.data_ptr() if host.n_long else None
         s.n_long, s.n_slots, s.tag = host.n_long, host.n_slots, int(tag)
-        s.engine, s.unroll = -2, 0  # gather engine chosen per call from operand size and K (spmm.cu)
+        # gather engine: -2 = chosen per call from operand size and K (spmm.cu pick_engine); an engine may force one
+        # (Engine.spmm_engine, GCNB_SPMM_ENGINE: parity tests run every engine through the whole model on small graphs)
+        s.engine, s.unroll = int(getattr(eng, "spmm_engine", -2)), 0
         self.struct = s
         self.refill(eng, host)
 
@@ -303,6 +305,10 @@ class Engine:
         # (measured on C3: 1024 columns at >= 5% density; 1536 columns save 1.1 ms of SpMM and cost 2.1 ms of GEMM)
         self.hot_density = float(os.environ.get("GCNB_HOT_DENSITY", "0.05") if hot_density is None else hot_density)
         self.hot_max = int(os.environ.get("GCNB_HOT_MAX", "1024") if hot_max is None else hot_max)
+        # test / tuning knobs: force one SpMM gather engine for every product (-2 = per-call choice) and the number of
+        # column ranges the rows of X^T are cut into (0 = from the panel working-set rule)
+        self.spmm_engine = int(os.environ.get("GCNB_SPMM_ENGINE", "-2"))
+        self.xt_blocks = int(os.environ.get("GCNB_XT_BLOCKS", "0"))
         self.group = group
         self.world = torch.distributed.get_world_size(group) if group is not None else 1
         self.rank = torch.distributed.get_rank(group) if group is not None else 0
@@ -435,7 +441,7 @@ class Engine:
             self.copy_ctx.sync()
             self._uploads = {}
             hg = HostGraph(X, A, self.world, self.rank, self.spmm_chunk, need_backward, assume_symmetric,
-                           self.hot_density, self.hot_max)
+                           self.hot_density, self.hot_max, self.xt_blocks)
             self.host = hg
             self.n, self.n_pad, self.r0, self.r1 = hg.n, hg.n_pad, hg.r0, hg.r1
             self.n_loc, self.n_tot, self.symmetric = hg.n_loc, hg.n_tot, hg.symmetric

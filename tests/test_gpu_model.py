@@ -216,3 +216,34 @@ def test_uncached_inputs_reupload_gives_identical_results(problem):
     r = gcn_ref.loss_and_grads(params, X2, A2, Y, tr, hid, True, None, 0.0)
     assert l0 != l1
     np.testing.assert_allclose(l1, r["train_loss"], rtol=1e-3)
+
+
+@pytest.mark.parametrize("engine,xt_blocks", [(0, 1), (1, 2), (2, 4)])
+def test_whole_model_parity_with_every_spmm_engine(problem, monkeypatch, engine, xt_blocks):
+    """The per-call engine choice picks the L2-panel engine and the column-blocked X^T plan only for operands far larger
+    than this test graph, so force each engine (and a blocked plan) through the whole model: predict, one training step
+    and every gradient against the oracle."""
+    monkeypatch.setenv("GCNB_SPMM_ENGINE", str(engine))
+    monkeypatch.setenv("GCNB_XT_BLOCKS", str(xt_blocks))
+    A, X, Y, tr, dev, te, cfg = problem
+    hid = [300, 300, 300]
+    clf = _model(cfg, True, hid=hid)
+    clf.build_model(A, seed=21)
+    params = [p.copy() for p in clf.init_params]
+    preds, probs = clf.predict(X, A, te)
+    eng = clf._get_engine()
+    assert eng.spmm_engine == engine and eng.A.engine_for(eng, eng.ldh[0], hid[0]) == engine
+    rp, rprob = gcn_ref.predict(params, X, A, te, hid, True)
+    np.testing.assert_allclose(probs, rprob, rtol=1e-3, atol=1e-7)
+    ok = _confident(rprob)
+    np.testing.assert_array_equal(preds[ok], rp[ok])
+    seed = 777
+    out = clf.f_train(X, Y[tr], Y[dev], A, tr, dev, seed=seed, update=False)
+    assert eng.host.XT.col_blocks == xt_blocks
+    keep = gcn_ref.dropout_keep_mask(seed, cfg["n"], hid[0], 0.5)
+    r = gcn_ref.loss_and_grads(params, X, A, Y, tr, hid, True, keep.astype(np.float32) / 0.5, 0.0, dtype="float64",
+                               dev_idx=dev)
+    np.testing.assert_allclose(out[0], r["train_loss"], rtol=1e-3)
+    np.testing.assert_allclose(out[2], r["dev_loss"], rtol=1e-3)
+    for name, g, rg in zip([e["name"] for e in eng.layout.entries], eng.get_grads(), r["grads"]):
+        np.testing.assert_allclose(g, rg, rtol=1e-3, atol=1e-4 * float(np.abs(rg).max()) + 1e-12, err_msg=name)
