@@ -58,7 +58,7 @@ struct SpmmParams {
   int* counter;
   int pcol0;       // first column of this pass inside a partial slot (0 unless the slots span all of K: panel engine)
   int k4;          // K rounded up to 4 (panel engine: the panels tile [0, k4))
-  int evict_last;  // panel engine: gathers carry an L2 evict_last hint
+  int evict_last;  // panel engine, gather cache policy: 0 default, 1 L2 evict_last hint, 2 the same with L1 allocation
   int col_base;    // panel engine: first column of panel 0 of this launch
 };
 
@@ -427,7 +427,7 @@ __device__ __forceinline__ void panel_epilogue(const SpmmParams& p, int row, int
 }
 
 // GL lanes per row item (panel = 4*GL floats), R (column, value) pairs per lane and batch: GL*R gathers in flight.
-// KEEP: gathers carry an L2 evict_last hint.  Batches in which every item of the warp still has GL*R nonzeros run
+// KEEP: gather cache policy (0 default, 1 L2 evict_last hint, 2 the same with L1 allocation).  Batches in which every item of the warp still has GL*R nonzeros run
 // without predicates (plans sorted by item length make that the common case); the rest take the predicated tail.
 template <int GL, int R, int KEEP>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, GL * R <= 8 ? 4 : 2) spmm_panel_kernel(const SpmmParams p) {
@@ -640,10 +640,10 @@ void launch_softmax(gcnb_ctx* ctx, const SpmmParams& p, int n_rows) {
 
 // engine 2: every column panel of the product in one launch (panel-major), then the long-row fix-up and, when
 // asked for, the row softmax as a pass of its own
-int launch_panels(gcnb_ctx* ctx, const SpmmParams& p0, int n_rows, int K4, int unroll, bool A_engine_auto) {
+int launch_panels(gcnb_ctx* ctx, const SpmmParams& p0, int n_rows, int K4, int unroll, bool auto_width) {
   int PW = ctx->spmm_panel;
   if (PW != 16 && PW != 64) PW = 32;
-  if (A_engine_auto) PW = 32;
+  if (auto_width) PW = 32;
   SpmmParams p = p0;
   p.softmax = 0;
   p.logits = nullptr;

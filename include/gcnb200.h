@@ -69,8 +69,8 @@ int gcnb_set_stream(gcnb_ctx* ctx, void* stream);
 void* gcnb_get_stream(const gcnb_ctx* ctx);
 int gcnb_set_workspace(gcnb_ctx* ctx, void* dev_ptr, size_t bytes);
 /* named integer options: "spmm_variant" (0 = LDG.128 register gather, 1 = bulk-copy/TMA staged, 2 = L2-resident
- * column panels), "spmm_panel" (panel width of engine 2 in floats: 16, 32, 64), "spmm_panel_policy" (1 = panel
- * gathers carry an L2 evict_last hint),
+ * column panels), "spmm_panel" (panel width of engine 2 in floats: 16, 32, 64), "spmm_panel_policy" (panel gathers: 0 =
+ * default cache policy, 1 = L2 evict_last hint (default), 2 = evict_last with L1 allocation),
  * "spmm_unroll" (nonzeros gathered per batch), "gemm_tc" (1 = tcgen05 path where supported, the
  * default), "tc_launches" (read-only count of tcgen05 kernels launched), "sm_margin" (SMs the persistent
  * SpMM kernel leaves to concurrently running collectives). */
