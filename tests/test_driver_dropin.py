@@ -141,3 +141,34 @@ def test_unchanged_reference_driver_runs_on_the_dropin(oracle_engine, tmp_path, 
         weights = pickle.load(f)
     assert [w.shape for w in weights] == [(120, 16), (16,), (16, 16), (16,), (16, 16), (16,), (16, 16), (16,),
                                           (16, 16), (16,), (16, 6), (6,)]
+
+
+def test_dump_and_weight_pickles_round_trip(tmp_path):
+    """geographconv_b200.io: dump.pkl in the reference's gzip+pickle format (data.py:28-34) and the input assembly of
+    gcnmain.main (gcnmain.py:153-212); a Python-2 style pickle (latin1 bytes) loads through the fallback."""
+    import gzip
+    from geographconv_b200 import io as gio
+    data = synth.synthetic_dump(SMALL)
+    fn = str(tmp_path / "dump.pkl")
+    gio.dump_obj(data, fn)
+    with gzip.open(fn, "rb") as f:                      # what the reference's load_obj does
+        back = pickle.load(f)
+    assert len(back) == 13 and (back[0] != data[0]).nnz == 0 and (back[2] == data[2]).all()
+    got = gio.assemble(gio.load_obj(fn))
+    A, X_tr, Y_tr, X_dev, Y_dev, X_te, Y_te = data[:7]
+    n_tr, n_dev, n_te = X_tr.shape[0], X_dev.shape[0], X_te.shape[0]
+    assert got["X"].format == "csr" and got["X"].dtype == np.float32 and got["A"].dtype == np.float32
+    assert got["X"].shape == (n_tr + n_dev + n_te, X_tr.shape[1]) and got["Y"].dtype == np.int32
+    assert (got["X"][n_tr:n_tr + n_dev] != X_dev.astype(np.float32)).nnz == 0
+    np.testing.assert_array_equal(got["Y"], np.concatenate([Y_tr, Y_dev, Y_te]))
+    np.testing.assert_array_equal(got["dev_indices"], np.arange(n_tr, n_tr + n_dev))
+    np.testing.assert_array_equal(got["test_indices"], np.arange(n_tr + n_dev, n_tr + n_dev + n_te))
+    assert got["train_indices"].dtype == np.int32 and got["output_size"] == int(max(Y_tr.max(), Y_dev.max(), Y_te.max())) + 1
+    with pytest.raises(ValueError):
+        gio.assemble(data[:12])
+    # a pickle holding non-ASCII byte strings the way Python 2 wrote them: protocol 2, str opcode with raw bytes
+    py2 = b"\x80\x02U\x04caf\xe9q\x00."                 # pickle.dumps('caf\xe9') under Python 2
+    fn2 = str(tmp_path / "py2.pkl")
+    with gzip.open(fn2, "wb") as f:
+        f.write(py2)
+    assert gio.load_obj(fn2) == "caf\xe9"
