@@ -463,20 +463,22 @@ def residual_dense(x, A, W=None, b=None, nonlinearity='selu', device=None):
 
 
 def np_softmax(x):
-    """gcnmodel.py:298-301 (softmax over ALL entries of x, as the reference writes it)."""
-    e_x = np.exp(x - np.max(x))
-    return e_x / e_x.sum()
+    """Softmax over ALL entries of ``x`` jointly, which is what gcnmodel.py:298-301 computes (no axis argument)."""
+    x = np.asarray(x)
+    shifted = np.exp(x - x.max())
+    return shifted / shifted.sum()
 
 
 def iterate_minibatches(inputs, targets, batchsize, shuffle=False):
-    """gcnmodel.py:303-313."""
-    assert inputs.shape[0] == targets.shape[0]
+    """Yield (inputs, targets) slices of ``batchsize`` rows; a trailing partial batch is dropped and ``shuffle`` draws
+    one permutation from the global NumPy stream (behaviour of gcnmodel.py:303-313; ``GraphConv`` trains full-batch and
+    never calls it)."""
+    n = inputs.shape[0]
+    assert n == targets.shape[0]
+    order = None
     if shuffle:
-        indices = np.arange(inputs.shape[0])
-        np.random.shuffle(indices)
-    for start_idx in range(0, inputs.shape[0] - batchsize + 1, batchsize):
-        if shuffle:
-            excerpt = indices[start_idx:start_idx + batchsize]
-        else:
-            excerpt = slice(start_idx, start_idx + batchsize)
-        yield inputs[excerpt], targets[excerpt]
+        order = np.arange(n)
+        np.random.shuffle(order)
+    for lo in range(0, n - batchsize + 1, batchsize):
+        sel = slice(lo, lo + batchsize) if order is None else order[lo:lo + batchsize]
+        yield inputs[sel], targets[sel]
