@@ -55,9 +55,10 @@ class OracleEngine:
         f = gcn_ref.forward(self.params, self.X, self.A, self.layout.hid, self.layout.highway, None, self.nonlin)
         self.P, self._gates = f["probs"], f["gates"]
 
-    def gather_predictions(self, idx):
+    def gather_predictions(self, idx, want_probs=True):
         rows = self.P[np.asarray(idx, dtype=np.int64)]
-        return rows.argmax(-1).astype(np.int64), rows.astype(np.float32)
+        preds = rows.argmax(-1).astype(np.int64)
+        return (preds, rows.astype(np.float32)) if want_probs else (preds, preds)  # no device here: host array twice
 
     def read_matrix(self, buf, rows, cols):
         return np.asarray(buf)[:rows, :cols]

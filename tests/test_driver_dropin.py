@@ -143,6 +143,20 @@ def test_unchanged_reference_driver_runs_on_the_dropin(oracle_engine, tmp_path, 
                                           (16, 16), (16,), (16, 6), (6,)]
 
 
+def test_predict_classes_equals_predict_without_probabilities(oracle_engine):
+    """GraphConv.predict_classes: same argmax as predict (gcnmodel.py:452-454), no probability rows returned."""
+    from geographconv_b200.gcnmodel import GraphConv
+    A, X, Y, tr, dev, te, cfg = synth.synthetic_problem(SMALL)
+    clf = GraphConv(cfg["f"], cfg["classes"], cfg["hid"], 0.0, 0.5)
+    clf.build_model(A, seed=1)
+    preds, probs = clf.predict(X, A, te)
+    p2, handle = clf.predict_classes(X, A, te)
+    np.testing.assert_array_equal(preds, p2)
+    assert p2.dtype == np.int64 and len(handle) == len(te)
+    with pytest.raises(ValueError, match="must be sparse"):
+        clf.predict_classes(X.toarray(), A, te)
+
+
 def test_dump_and_weight_pickles_round_trip(tmp_path):
     """geographconv_b200.io: dump.pkl in the reference's gzip+pickle format (data.py:28-34) and the input assembly of
     gcnmain.main (gcnmain.py:153-212); a Python-2 style pickle (latin1 bytes) loads through the fallback."""
