@@ -77,8 +77,8 @@ def normalized_adjacency_from_edges(u, v, n, device=None):
 
 def normalize_adjacency(adj, dtype="float32", device=None):
     """Drop-in for gcnmain.py:117-128: ``adj`` is the symmetric 0/1 adjacency (any SciPy sparse format) of the
-    undirected graph; returns A_hat as float32 CSR.  Weighted or asymmetric inputs are rejected (the reference graph
-    is an unweighted ``nx.Graph``)."""
+    undirected graph; returns A_hat as float32 CSR.  Edge weights (``nx.adjacency_matrix(..., weight='w')``,
+    gcnmain.py:115) go through ``normalize_weighted_adjacency``; asymmetric inputs are rejected (``nx.Graph``)."""
     if dtype != "float32":
         raise ValueError("the B200 path produces float32 (gcnmain.py:167 fixes dtype to float32)")
     adj = sp.coo_matrix(adj)
@@ -87,7 +87,7 @@ def normalize_adjacency(adj, dtype="float32", device=None):
     n = adj.shape[0]
     keep = adj.data != 0
     if not np.all(adj.data[keep] == 1):
-        raise NotImplementedError("weighted adjacency: the reference graph carries no 'w' attributes (data.py:56,61)")
+        return normalize_weighted_adjacency(adj, device=device)
     u, v = adj.row[keep], adj.col[keep]
     A = normalized_adjacency_from_edges(u, v, n, device=device)
     # an asymmetric input would have been symmetrised by the edge-list builder: refuse instead of guessing
@@ -96,4 +96,40 @@ def normalize_adjacency(adj, dtype="float32", device=None):
     off_diag = pat.nnz - int(np.count_nonzero(pat.diagonal()))
     if A.nnz != off_diag + n:
         raise ValueError("adjacency is not symmetric")
+    return A
+
+
+def normalize_weighted_adjacency(adj, device=None):
+    """gcnmain.py:115-128 for a graph whose edges carry weights: ``adj`` is the symmetric weighted adjacency SciPy matrix
+    ``nx.adjacency_matrix(graph, weight='w')`` returns.  The diagonal is forced to 1 on the host (``setdiag(0)``;
+    ``setdiag(1)`` are structure edits); row sums, ``1/sqrt`` (inf -> 0) and ``D * adj * D`` run on the GPU in float64
+    with one rounding to float32 (``gcnb_adj_normalize_weighted_f64``).  Returns float32 CSR, columns ascending."""
+    d = get_dev(device)
+    W = sp.csr_matrix(adj, dtype=np.float64, copy=True)
+    if W.shape[0] != W.shape[1]:
+        raise ValueError("adjacency must be square")
+    n = W.shape[0]
+    if n >= 2**31 - 1 or W.nnz + n >= 2**31 - 1:
+        raise ValueError("adjacency must fit int32 indices")
+    W.sum_duplicates()
+    D = (W - W.T).tocsr()
+    if D.nnz and float(np.abs(D.data).max()) != 0.0:
+        raise ValueError("adjacency is not symmetric")
+    W.setdiag(1.0)  # setdiag(0) then setdiag(1): every diagonal entry present and equal to 1
+    W = W.tocsr()
+    W.sort_indices()
+    rowptr = np.ascontiguousarray(W.indptr, dtype=np.int32)
+    col = np.ascontiguousarray(W.indices, dtype=np.int32)
+    dr, dc, dw = d.upload(rowptr), d.upload(col), d.upload(np.ascontiguousarray(W.data, dtype=np.float64))
+    dinv = torch.empty(max(n, 1), dtype=torch.float64, device=d.dev)
+    val = torch.empty(max(W.nnz, 1), dtype=torch.float32, device=d.dev)
+    d.fence()
+    p = lambda t: C.c_void_p(t.data_ptr())
+    d.ctx.call("gcnb_adj_normalize_weighted_f64", p(dr), p(dc), p(dw), n, p(dinv), p(val))
+    h_val = np.empty(W.nnz, dtype=np.float32)
+    if W.nnz:
+        d.ctx.call("gcnb_d2h", C.c_void_p(h_val.ctypes.data), p(val), h_val.nbytes)
+    d.ctx.sync()
+    A = sp.csr_matrix((h_val, col, rowptr), shape=(n, n))
+    A.has_sorted_indices = True
     return A

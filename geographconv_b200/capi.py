@@ -93,6 +93,7 @@ SIGNATURES = {
     "gcnb_adj_workspace_bytes": (_sz, [_i64, _i32]),
     "gcnb_adj_build_rows": (C.c_int, [_ctxp, _vp, _vp, _i64, _i32, _vp, _sz, _vp, C.POINTER(_i64)]),
     "gcnb_adj_fill_f32": (C.c_int, [_ctxp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "gcnb_adj_normalize_weighted_f64": (C.c_int, [_ctxp, _vp, _vp, _vp, _i32, _vp, _vp]),
 }
 
 _lib = None

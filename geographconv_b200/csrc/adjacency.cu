@@ -460,3 +460,44 @@ extern "C" int gcnb_adj_fill_f32(gcnb_ctx* ctx, int64_t n_edges, int32_t n_nodes
   GCNB_LAUNCHED(ctx);
   return GCNB_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// weighted graphs: nx.adjacency_matrix(..., weight='w') (gcnmain.py:115) yields edge weights when edges carry a
+// 'w' attribute.  The caller hands the symmetric weighted CSR with its unit diagonal already in place
+// (setdiag(0); setdiag(1), gcnmain.py:117-120 -- structure edits); the row sums, 1/sqrt and the two-sided scaling
+// (gcnmain.py:122-128) run here in the reference's float64 with one final rounding to float32.
+// ---------------------------------------------------------------------------------------
+namespace {
+// one thread per row: the float64 sum runs over the row in stored order, like SciPy's csr_matvec behind adj.sum(axis=1)
+__global__ void adjw_dinv_kernel(const int* __restrict__ rowptr, const double* __restrict__ w, int n, double* dinv) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  double s = 0.0;
+  for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) s = __dadd_rn(s, w[k]);
+  const double d = 1.0 / sqrt(s);
+  dinv[r] = isinf(d) ? 0.0 : d;  // diags_sqrt[isinf] = 0 (gcnmain.py:124)
+}
+__global__ void adjw_scale_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ w,
+                                  const double* __restrict__ dinv, int n, float* val) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= n) return;
+  const double di = dinv[r];
+  for (int k = rowptr[r] + lane; k < rowptr[r + 1]; k += 32)
+    val[k] = (float)__dmul_rn(__dmul_rn(di, w[k]), dinv[col[k]]);  // (D * adj) * D, then astype(float32)
+}
+}  // namespace
+
+extern "C" int gcnb_adj_normalize_weighted_f64(gcnb_ctx* ctx, const int32_t* rowptr, const int32_t* colidx,
+                                               const double* weights, int32_t n_nodes, double* dinv_work, float* val) {
+  if (!ctx) return GCNB_E_INVALID;
+  GCNB_REQUIRE(ctx, n_nodes >= 0, "negative size");
+  if (n_nodes == 0) return GCNB_OK;
+  GCNB_REQUIRE(ctx, rowptr && colidx && weights && dinv_work && val, "null pointer");
+  ProfScope scope(ctx, GCNB_TAG_ELEM);
+  adjw_dinv_kernel<<<cdiv(n_nodes, 256), 256, 0, ctx->stream>>>(rowptr, weights, n_nodes, dinv_work);
+  GCNB_LAUNCHED(ctx);
+  adjw_scale_kernel<<<cdiv(n_nodes, 8), 256, 0, ctx->stream>>>(rowptr, colidx, weights, dinv_work, n_nodes, val);
+  GCNB_LAUNCHED(ctx);
+  return GCNB_OK;
+}

@@ -839,8 +839,14 @@ bool gcnb_wgrad_tc_supported(const gcnb_ctx* ctx, int M, int N, int K, int lda, 
 }
 
 size_t gcnb_wgrad_tc_workspace_bytes(int M, int N, int K) {
-  const WgPlan w = wgrad_plan(148, M, N, K);
-  return (size_t)(w.splits + 1) * M * N * sizeof(float);
+  // no context here (the ABI sizes workspaces before a context exists): bound the split count by the largest SM
+  // count any sm_100 part has instead of assuming 148; the launch plans with ctx->sm_count and needs no more than this
+  const WgPlan w = wgrad_plan(256, M, N, K);
+  const int tiles = w.m_tiles * w.n_tiles;
+  int max_splits = tiles > 0 ? 256 / tiles : 1;
+  if (max_splits < w.splits) max_splits = w.splits;
+  if (max_splits < 1) max_splits = 1;
+  return (size_t)(max_splits + 1) * M * N * sizeof(float);
 }
 
 int gcnb_wgrad_tc(gcnb_ctx* ctx, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,

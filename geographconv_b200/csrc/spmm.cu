@@ -545,6 +545,52 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) row_softmax_kernel(const Sp
   spmm_epilogue<NCHUNK>(p, row, acc, lane);
 }
 
+// row softmax in place over rows wider than one register pass (K > 512: TwitterWorld has 930 classes at bucket 2400,
+// reference README.md:177-181).  C already holds product + bias; three sweeps over the row (max, sum of exp,
+// normalise), the row stays in L1/L2 between them.  Padding columns are written as zeros.
+__global__ void __launch_bounds__(kWarpsPerCta * 32) row_softmax_wide_kernel(const SpmmParams p, int n_rows) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  float4* crow = reinterpret_cast<float4*>(p.C + (size_t)row * p.ldc);
+  float4* lrow = p.logits ? reinterpret_cast<float4*>(p.logits + (size_t)row * p.ldc) : nullptr;
+  const int nf4 = p.k4 >> 2;
+  float m = -INFINITY;
+  for (int f4 = lane; f4 < nf4; f4 += 32) {
+    float4 x = crow[f4];
+    const int c = 4 * f4;
+    if (c + 1 >= p.K) x.y = 0.f;
+    if (c + 2 >= p.K) x.z = 0.f;
+    if (c + 3 >= p.K) x.w = 0.f;
+    if (lrow) lrow[f4] = x;
+    m = fmaxf(m, x.x);
+    if (c + 1 < p.K) m = fmaxf(m, x.y);
+    if (c + 2 < p.K) m = fmaxf(m, x.z);
+    if (c + 3 < p.K) m = fmaxf(m, x.w);
+  }
+  m = warp_max(m);
+  float s = 0.f;
+  for (int f4 = lane; f4 < nf4; f4 += 32) {
+    const float4 x = crow[f4];
+    const int c = 4 * f4;
+    s += expf(x.x - m);
+    if (c + 1 < p.K) s += expf(x.y - m);
+    if (c + 2 < p.K) s += expf(x.z - m);
+    if (c + 3 < p.K) s += expf(x.w - m);
+  }
+  s = warp_sum(s);
+  for (int f4 = lane; f4 < nf4; f4 += 32) {
+    const float4 x = crow[f4];
+    const int c = 4 * f4;
+    float4 o;
+    o.x = expf(x.x - m) / s;
+    o.y = c + 1 < p.K ? expf(x.y - m) / s : 0.f;
+    o.z = c + 2 < p.K ? expf(x.z - m) / s : 0.f;
+    o.w = c + 3 < p.K ? expf(x.w - m) / s : 0.f;
+    crow[f4] = o;
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // long rows: add the per-item partial sums in item order, then the epilogue
 // ---------------------------------------------------------------------------------------
@@ -785,7 +831,6 @@ extern "C" int gcnb_spmm_csr_f32(gcnb_ctx* ctx, const gcnb_csr* A, const float* 
   GCNB_REQUIRE(ctx, A->nnz == 0 || (A->colidx && A->val), "CSR arrays missing");
   GCNB_REQUIRE(ctx, A->n_long == 0 || A->long_rows, "long row table missing");
   if (epi) {
-    GCNB_REQUIRE(ctx, !epi->softmax || K <= kMaxPassCols, "softmax epilogue needs K <= 512");
     GCNB_REQUIRE(ctx, !epi->bias || aligned16(epi->bias), "bias must be 16-byte aligned");
     GCNB_REQUIRE(ctx, epi->dropout_p >= 0.f && epi->dropout_p < 1.f, "dropout_p in [0,1)");
     GCNB_REQUIRE(ctx, !epi->logits || aligned16(epi->logits), "logits must be 16-byte aligned");
@@ -820,8 +865,18 @@ extern "C" int gcnb_spmm_csr_f32(gcnb_ctx* ctx, const gcnb_csr* A, const float* 
     }
     p.seed = epi->seed; p.row0 = epi->row0; p.logits = epi->logits;
   }
-  if (engine == 2) return launch_panels(ctx, p, A->n_rows, K4, unroll, A->engine == -2);
-  for (int c0 = 0; c0 < K4; c0 += kMaxPassCols) {
+  // a row softmax over more than one register pass of columns runs as a pass of its own after the product + bias
+  const bool wide_softmax = p.softmax && K > kMaxPassCols;
+  float* const wide_logits = p.logits;
+  if (wide_softmax) {
+    p.softmax = 0;
+    p.logits = nullptr;
+  }
+  if (engine == 2) {
+    const int rc = launch_panels(ctx, p, A->n_rows, K4, unroll, A->engine == -2);
+    if (rc != GCNB_OK || !wide_softmax) return rc;
+  }
+  for (int c0 = 0; engine != 2 && c0 < K4; c0 += kMaxPassCols) {
     const int w = (K4 - c0) < kMaxPassCols ? (K4 - c0) : kMaxPassCols;
     p.col0 = c0;
     p.nf4 = w / 4;
@@ -835,6 +890,13 @@ extern "C" int gcnb_spmm_csr_f32(gcnb_ctx* ctx, const gcnb_csr* A, const float* 
       default: rc = launch_pass<4>(ctx, p, engine, unroll); break;
     }
     if (rc != GCNB_OK) return rc;
+  }
+  if (wide_softmax) {
+    p.col0 = 0;
+    p.k4 = K4;
+    p.logits = wide_logits;
+    row_softmax_wide_kernel<<<cdiv(A->n_rows, kWarpsPerCta), kWarpsPerCta * 32, 0, ctx->stream>>>(p, A->n_rows);
+    GCNB_LAUNCHED(ctx);
   }
   return GCNB_OK;
 }

@@ -112,6 +112,16 @@ def plan_col_blocks(rowptr, colidx, n_cols, n_blocks, chunk):
     return items, long_rows, n_slots
 
 
+def _fingerprint(M):
+    """Cheap content fingerprint of a SciPy sparse matrix (about 4096 strided samples of its value and index arrays):
+    an in-place edit of a cached X / A is noticed without hashing gigabytes on every call."""
+    M = M if hasattr(M, "indices") and hasattr(M, "data") else M.tocsr()
+    if M.nnz == 0:
+        return (0.0, 0)
+    step = max(1, M.nnz // 4096)
+    return (float(np.asarray(M.data[::step], dtype=np.float64).sum()), int(np.asarray(M.indices[::step], dtype=np.int64).sum()))
+
+
 class HostCsr:
     """Host-side CSR of one SpMM operand: int32 / fp32 arrays in pinned memory plus the row-item plan."""
 
@@ -146,7 +156,7 @@ class HostCsr:
         self.nbytes = sum(a.nbytes for a in (self.rowptr, self.colidx, self.val, self.items, self.long_rows))
 
 
-def split_hot_columns(Xl, min_density, max_cols):
+def split_hot_columns(Xl, min_density, max_cols, df=None, n_total=None):
     """Split CSR ``Xl`` into a dense block of its most frequent columns and the CSR of the rest.
 
     Bag-of-words columns are Zipf distributed: at C3 the 512 most frequent of 50k terms carry 63% of the
@@ -156,12 +166,17 @@ def split_hot_columns(Xl, min_density, max_cols):
     Returns (hot_cols int32[Kh] ascending, X_hot CSR n x Kh with hot-local column ids, X_cold CSR) or
     (None, None, Xl).  The hot block stays CSR on the host (a quarter of the dense bytes) and is expanded on the device
     (gcnb_csr_to_dense_f32).
+
+    ``df`` / ``n_total``: document frequencies and row count of the WHOLE matrix when ``Xl`` is one rank's row block.
+    Every rank then picks the same hot set, each row's sum is associated exactly as on one GPU and the row-partitioned
+    forward is bit-equal to the single-GPU forward.
     """
     n, f = Xl.shape
-    if n == 0 or Xl.nnz == 0 or max_cols < 32 or min_density <= 0:
+    if df is None:
+        df, n_total = np.bincount(Xl.indices, minlength=f), n
+    if n_total == 0 or int(df.sum()) == 0 or max_cols < 32 or min_density <= 0:
         return None, None, Xl
-    df = np.bincount(Xl.indices, minlength=f)
-    n_hot = int(np.count_nonzero(df >= min_density * n))
+    n_hot = int(np.count_nonzero(df >= min_density * n_total))
     kh = min(n_hot, int(max_cols)) // 32 * 32
     if kh < 64:
         return None, None, Xl
@@ -181,8 +196,19 @@ def split_hot_columns(Xl, min_density, max_cols):
     indptr = np.zeros(n + 1, dtype=np.int32)
     np.cumsum(counts, out=indptr[1:])
     X_cold = sp.csr_matrix((Xl.data[cold], Xl.indices[cold], indptr), shape=(n, f))
-    X_cold.has_sorted_indices = True
+    X_cold.has_sorted_indices = bool(Xl.has_sorted_indices)  # a subsequence of sorted rows is sorted; nothing else is
     return hot_cols, X_hot, X_cold
+
+
+def canonical_csr(M):
+    """CSR with ascending column ids and duplicate (row, column) entries summed -- what SciPy's and Theano's products
+    compute on a non-canonical matrix (the dense hot-column expansion and the sorted-plan kernels need it explicit).
+    Canonical inputs are returned as they are; others are copied, never edited in place (caller-owned)."""
+    M = M.tocsr()
+    if not M.has_canonical_format:
+        M = M.copy()
+        M.sum_duplicates()
+    return M
 
 
 class HostGraph:
@@ -192,7 +218,7 @@ class HostGraph:
     memory across epochs, gcnmain.py:172-179) and cached by the engine."""
 
     def __init__(self, X, A, world, rank, chunk, need_backward, assume_symmetric=None, hot_density=0.0,
-                 hot_max=0, xt_blocks=0):
+                 hot_max=0, xt_blocks=0, allreduce=None):
         n = X.shape[0]
         self.n = n
         self.n_pad, blocks = row_blocks(n, world)
@@ -210,7 +236,13 @@ class HostGraph:
             Xl, Al = slice_rows(X, self.r0, self.r1), widen(slice_rows(A, self.r0, self.r1))
         else:
             Xl, Al = X.tocsr(), A.tocsr()
-        self.hot_cols, X_hot, Xl = split_hot_columns(Xl, hot_density, hot_max)
+        Xl, Al = canonical_csr(Xl), canonical_csr(Al)
+        df = None
+        if world > 1 and hot_max >= 32 and hot_density > 0:
+            # same hot set on every rank: document frequencies summed over the row blocks
+            df = np.bincount(Xl.indices, minlength=Xl.shape[1]).astype(np.int64)
+            df = allreduce(df) if allreduce is not None else df
+        self.hot_cols, X_hot, Xl = split_hot_columns(Xl, hot_density, hot_max, df, n)
         self.kh = 0 if self.hot_cols is None else len(self.hot_cols)
         self.hot_cols_p = _pinned(self.hot_cols) if self.kh else None
         self.hot_ptr = _pinned(np.ascontiguousarray(X_hot.indptr, dtype=np.int32)) if self.kh else None
@@ -346,6 +378,7 @@ class Engine:
         self.adam_state = torch.zeros(2, dtype=torch.float32, device=self.dev)
         # metrics: train {loss_sum, n_correct}, dev {loss_sum, n_correct}, reg_sum, pad
         self.metrics = torch.zeros(8, dtype=torch.float32, device=self.dev)
+        self.metrics_sum = torch.zeros(8, dtype=torch.float32, device=self.dev)
         self.metrics_host = torch.zeros(8, dtype=torch.float32).pin_memory()
         self._fence()
         self.ws = None
@@ -353,6 +386,7 @@ class Engine:
         self.n = None  # rows bound (global)
         self.A = self.X = self.XT = self.AT = None
         self._bound_key = None
+        self._bound_refs = None
         self.host = None
         self._idx_cache = {}
         self.h2d_bytes_last_bind = 0
@@ -428,7 +462,9 @@ class Engine:
         """
         if not sp.issparse(X) or not sp.issparse(A):
             raise ValueError("Input for this layer must be sparse")  # gcnmodel.py:34-36
-        key = (id(X), X.shape, X.nnz, id(A), A.shape, A.nnz)
+        # identity + shape + nnz + a strided content fingerprint; the engine also keeps references to the bound
+        # objects, so an id cannot be handed to a new matrix while its device copy is cached
+        key = (id(X), X.shape, X.nnz, id(A), A.shape, A.nnz, _fingerprint(X), _fingerprint(A))
         same = self._bound_key == key and (self.host.need_backward or not need_backward)
         if same and not force_upload:
             return
@@ -441,8 +477,9 @@ class Engine:
             self.copy_ctx.sync()
             self._uploads = {}
             hg = HostGraph(X, A, self.world, self.rank, self.spmm_chunk, need_backward, assume_symmetric,
-                           self.hot_density, self.hot_max, self.xt_blocks)
+                           self.hot_density, self.hot_max, self.xt_blocks, allreduce=self._allreduce_host)
             self.host = hg
+            self._bound_refs = (X, A)
             self.n, self.n_pad, self.r0, self.r1 = hg.n, hg.n_pad, hg.r0, hg.r1
             self.n_loc, self.n_tot, self.symmetric = hg.n_loc, hg.n_tot, hg.symmetric
             self.X = DeviceCsr(self, hg.X, capi.TAG_SPMM_X)
@@ -484,6 +521,15 @@ class Engine:
         self.ctx.sync()
         self.copy_ctx.sync()
         self._bound_key = None
+        self._bound_refs = None
+
+    def _allreduce_host(self, arr):
+        """Sum a small host int64 array over the ranks (NCCL moves device memory only)."""
+        if self.world == 1:
+            return arr
+        t = torch.from_numpy(np.ascontiguousarray(arr)).to(self.dev)
+        torch.distributed.all_reduce(t, group=self.group)
+        return t.cpu().numpy()
 
     def _upload_hot(self, hg, ctx=None):
         ctx = self.ctx if ctx is None else ctx
@@ -563,9 +609,11 @@ class Engine:
             labels = np.asarray(labels)
             if len(labels) != len(idx):
                 raise AssertionError("inputs and targets differ in length")  # gcnmodel.py:304
-        key = (idx.ctypes.data, idx.shape, None if labels is None else labels.ctypes.data)
+        # keyed on the content (index sets are a few MB at most): fit() builds Y[train_indices] afresh on every call and
+        # malloc hands the same address to different label vectors, so addresses identify nothing
+        key = (idx.shape, idx.dtype.str, hash(idx.tobytes()), None if labels is None else hash(labels.tobytes()))
         hit = self._idx_cache.get(key)
-        if hit is not None and np.array_equal(hit[3], idx):
+        if hit is not None and np.array_equal(hit[3], idx) and (labels is None or np.array_equal(hit[6], labels)):
             if force_upload:
                 for dst, src in ((hit[0], hit[4]), (hit[1], hit[5])):
                     if dst is not None and src.size:
@@ -583,7 +631,9 @@ class Engine:
         d_lab = self.upload(ll) if have_labels else None
         self.ctx.sync()
         self._keepalive = []
-        self._idx_cache[key] = (d_idx, d_lab, len(li), idx.copy(), li, ll)
+        if len(self._idx_cache) >= 16:
+            self._idx_cache.pop(next(iter(self._idx_cache)))
+        self._idx_cache[key] = (d_idx, d_lab, len(li), idx.copy(), li, ll, labels.copy() if have_labels else None)
         return d_idx, d_lab, len(li)
 
     # ------------------------------------------------------------------ ops
@@ -831,10 +881,13 @@ class Engine:
 
     def read_metrics(self):
         """(train_loss, train_acc, dev_loss, dev_acc) of the last train_step; blocks."""
-        if self.world > 1:
+        src = self.metrics
+        if self.world > 1:  # sum over ranks in a scratch copy: a second read of the same step must not double it
             with torch.cuda.stream(self.stream):
-                torch.distributed.all_reduce(self.metrics[:4], group=self.group)
-        self.ctx.call("gcnb_d2h", C.c_void_p(self.metrics_host.data_ptr()), _ptr(self.metrics), 32)
+                self.metrics_sum.copy_(self.metrics)
+                torch.distributed.all_reduce(self.metrics_sum[:4], group=self.group)
+            src = self.metrics_sum
+        self.ctx.call("gcnb_d2h", C.c_void_p(self.metrics_host.data_ptr()), _ptr(src), 32)
         self.ctx.sync()
         m = self.metrics_host.numpy()
         nt, nd = max(self._n_train, 1), max(self._n_dev, 1)

@@ -46,8 +46,8 @@ class _Dev:
 
     def upload(self, arr):
         arr = np.ascontiguousarray(arr)
-        t = torch.empty(arr.size, dtype={np.dtype("float32"): torch.float32, np.dtype("int32"): torch.int32}[arr.dtype],
-                        device=self.dev)
+        t = torch.empty(arr.size, dtype={np.dtype("float32"): torch.float32, np.dtype("int32"): torch.int32,
+                                         np.dtype("float64"): torch.float64}[arr.dtype], device=self.dev)
         if arr.size:
             self.ctx.call("gcnb_h2d", C.c_void_p(t.data_ptr()), C.c_void_p(arr.ctypes.data), arr.nbytes)
         return t
@@ -211,8 +211,10 @@ def graph_conv_dense(A, x, W, b, act="tanh", device=None):
     q = gemm(x, W, device=device) if W is not None else np.asarray(x, dtype=np.float32)
     if A is None:
         if act == "softmax":
-            z = q + (0 if b is None else np.asarray(b)[None, :])
-            raise ValueError("softmax without a graph is not a GCN layer; pass A")
+            # the reference skips the convolution when A is falsy and still returns softmax(x.W + b)
+            # (gcnmodel.py:152-157): the same fused bias + row-softmax epilogue behind an identity graph
+            eye = sp.identity(q.shape[0], dtype=np.float32, format="csr")
+            return spmm(eye, q, bias=b, softmax=True, device=device)
         return gemm(q, np.eye(q.shape[1], dtype=np.float32), bias=b, act=act, device=device)
     if act == "softmax":
         return spmm(A, q, bias=b, softmax=True, device=device)

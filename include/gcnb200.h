@@ -132,7 +132,8 @@ int gcnb_csr_plan(const int32_t* host_rowptr, int32_t n_rows, int32_t chunk, int
 typedef struct gcnb_epilogue {
   const float* bias;   /* device, K floats padded to a multiple of 4 with zeros; or NULL */
   int32_t act;         /* gcnb_act */
-  int32_t softmax;     /* 1: row softmax over the K columns after the bias (K <= 512) */
+  int32_t softmax;     /* 1: row softmax over the K columns after the bias (fused up to K = 512; wider rows, e.g. the 930
+                        * classes of TwitterWorld, take a row pass of their own after the product) */
   int32_t accumulate;  /* 0: C = out.  1: C += out.  2: C = epilogue(C + A.B): the product is added to what C
                         * already holds BEFORE bias / activation / dropout / softmax */
   float dropout_p;     /* 0: none.  Inverted dropout, scale 1/(1-p) (lasagne DropoutLayer) */
@@ -271,6 +272,13 @@ int gcnb_adj_build_rows(gcnb_ctx* ctx, const int32_t* u, const int32_t* v, int64
                         void* work, size_t work_bytes, int32_t* rowptr, int64_t* nnz_host);
 int gcnb_adj_fill_f32(gcnb_ctx* ctx, int64_t n_edges, int32_t n_nodes, const void* work, const int32_t* rowptr,
                       int32_t* colidx, float* val);
+
+/* Weighted graphs (nx.adjacency_matrix(..., weight='w'), gcnmain.py:115): `rowptr` / `colidx` / `weights` (device,
+ * float64 like the SciPy matrix networkx returns) hold the symmetric weighted adjacency with its unit diagonal
+ * already in place (gcnmain.py:117-120); val[k] = float32((d_i * w_k) * d_j), d = 1/sqrt(row sum) in float64, inf -> 0
+ * (gcnmain.py:121-128).  `dinv_work`: n_nodes doubles of scratch. */
+int gcnb_adj_normalize_weighted_f64(gcnb_ctx* ctx, const int32_t* rowptr, const int32_t* colidx, const double* weights,
+                                    int32_t n_nodes, double* dinv_work, float* val);
 
 #ifdef __cplusplus
 }

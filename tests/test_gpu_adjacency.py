@@ -97,10 +97,27 @@ def test_normalize_adjacency_drop_in_and_errors():
     _same(A, gcn_ref.normalize_adjacency(adj))
     with pytest.raises(ValueError):
         adjacency.normalize_adjacency(sp.triu(adj, k=1))  # asymmetric
-    W = adj.astype(np.float64)
-    W.data[0] = 2.5
-    with pytest.raises(NotImplementedError):
-        adjacency.normalize_adjacency(W)
+    # weighted graph (nx.adjacency_matrix(..., weight='w'), gcnmain.py:115): integer weights sum exactly in float64,
+    # so the result is bit-identical to the oracle; real weights agree to the last float32 bit or one ulp (row-sum order)
+    T = sp.triu(adj, k=1).tocoo()
+    for weights, exact in ((rng.randint(1, 6, size=T.nnz).astype(np.float64), True), (rng.rand(T.nnz) + 0.25, False)):
+        U = sp.csr_matrix((weights, (T.row, T.col)), shape=(n, n))
+        W = (U + U.T).tocsr()
+        W.setdiag(7.0)  # replaced by the unit self loop
+        Aw = adjacency.normalize_adjacency(W)
+        ref = gcn_ref.normalize_adjacency(W)
+        if exact:
+            _same(Aw, ref)
+        else:
+            ref.sort_indices()
+            np.testing.assert_array_equal(Aw.indptr, ref.indptr)
+            np.testing.assert_array_equal(Aw.indices, ref.indices)
+            np.testing.assert_allclose(Aw.data, ref.data, rtol=1.2e-7, atol=0)
+        assert Aw.dtype == np.float32 and Aw.indices.dtype == np.int32
+    Wa = W.copy().tolil()
+    Wa[0, 1] = Wa[0, 1] + 1.0 if Wa[0, 1] else 3.0
+    with pytest.raises(ValueError):
+        adjacency.normalize_adjacency(Wa.tocsr())  # asymmetric weights
     with pytest.raises(ValueError):
         adjacency.normalized_adjacency_from_edges([0, 5], [1, 2], 4)
     # the C ABI itself refuses an out-of-range id (device-side check)

@@ -5,6 +5,7 @@ import scipy.sparse as sp
 
 from geographconv_b200 import synth
 from oracle import gcn_ref
+from parity_util import assert_argmax_parity
 
 pytestmark = pytest.mark.gpu
 
@@ -23,11 +24,6 @@ def problem():
     return synth.synthetic_problem(SMALL)
 
 
-def _confident(probs, margin=1e-4):
-    s = np.sort(probs, axis=1)
-    return (s[:, -1] - s[:, -2]) > margin * s[:, -1]
-
-
 @pytest.mark.parametrize("highway,hid", [(True, [300, 300, 300]), (False, [300, 200, 256]), (True, [64]),
                                          (True, [48] * 6)])
 def test_predict_matches_oracle(problem, highway, hid):
@@ -39,9 +35,10 @@ def test_predict_matches_oracle(problem, highway, hid):
     rp, rprob = gcn_ref.predict(params, X, A, te, hid, highway)
     assert preds.dtype == np.int64 and probs.dtype == np.float32 and probs.shape == (len(te), cfg["classes"])
     np.testing.assert_allclose(probs, rprob, rtol=1e-3, atol=1e-7)
-    ok = _confident(rprob)
-    np.testing.assert_array_equal(preds[ok], rp[ok])
-    assert ok.mean() > 0.9
+    # argmax on ALL rows against the float64 oracle; a mismatch is only tolerated on a numerical tie
+    _, rprob64 = gcn_ref.predict(params, X, A, te, hid, highway, dtype="float64")
+    n_mis, _ = assert_argmax_parity(preds, probs, rprob64)
+    assert n_mis <= 2, n_mis
     # logits (pre-softmax) parity: north_star's "logits within 1e-3"
     eng = clf._get_engine()
     eng.keep_logits = True
@@ -235,8 +232,8 @@ def test_whole_model_parity_with_every_spmm_engine(problem, monkeypatch, engine,
     assert eng.spmm_engine == engine and eng.A.engine_for(eng, eng.ldh[0], hid[0]) == engine
     rp, rprob = gcn_ref.predict(params, X, A, te, hid, True)
     np.testing.assert_allclose(probs, rprob, rtol=1e-3, atol=1e-7)
-    ok = _confident(rprob)
-    np.testing.assert_array_equal(preds[ok], rp[ok])
+    _, rprob64 = gcn_ref.predict(params, X, A, te, hid, True, dtype="float64")
+    assert_argmax_parity(preds, probs, rprob64)
     seed = 777
     out = clf.f_train(X, Y[tr], Y[dev], A, tr, dev, seed=seed, update=False)
     assert eng.host.XT.col_blocks == xt_blocks
@@ -247,3 +244,78 @@ def test_whole_model_parity_with_every_spmm_engine(problem, monkeypatch, engine,
     np.testing.assert_allclose(out[2], r["dev_loss"], rtol=1e-3)
     for name, g, rg in zip([e["name"] for e in eng.layout.entries], eng.get_grads(), r["grads"]):
         np.testing.assert_allclose(g, rg, rtol=1e-3, atol=1e-4 * float(np.abs(rg).max()) + 1e-12, err_msg=name)
+
+
+def test_wide_output_layer_930_classes(problem):
+    """TwitterWorld runs at bucket 2400 = 930 classes with 900 hidden units (reference README.md:177-181): the output
+    row is wider than one 512-column softmax pass."""
+    A, X, Y, tr, dev, te, cfg = problem
+    C = 930
+    hid = [96, 96]
+    from geographconv_b200.gcnmodel import GraphConv
+    clf = GraphConv(cfg["f"], C, hid, regul_coef=0.0, drop_out=0.0, highway=True, shard=False)
+    clf.build_model(A, seed=4)
+    params = [p.copy() for p in clf.init_params]
+    preds, probs = clf.predict(X, A, te)
+    _, rprob64 = gcn_ref.predict(params, X, A, te, hid, True, dtype="float64")
+    np.testing.assert_allclose(probs, rprob64, rtol=1e-3, atol=1e-8)
+    np.testing.assert_allclose(probs.sum(1), 1.0, rtol=1e-5)
+    assert_argmax_parity(preds, probs, rprob64)
+    Yw = (np.arange(cfg["n"]) % C).astype(np.int32)
+    out = clf.f_train(X, Yw[tr], Yw[dev], A, tr, dev, seed=1, update=False)
+    r = gcn_ref.loss_and_grads(params, X, A, Yw, tr, hid, True, None, 0.0, dtype="float64", dev_idx=dev)
+    np.testing.assert_allclose(out[0], r["train_loss"], rtol=1e-3)
+    eng = clf._get_engine()
+    for name, g, rg in zip([e["name"] for e in eng.layout.entries], eng.get_grads(), r["grads"]):
+        np.testing.assert_allclose(g, rg, rtol=1e-3, atol=1e-4 * float(np.abs(rg).max()) + 1e-12, err_msg=name)
+    # every SpMM engine takes the wide-softmax route
+    from geographconv_b200 import layers
+    q = np.random.RandomState(0).randn(cfg["n"], C).astype(np.float32)
+    b = np.random.RandomState(1).randn(C).astype(np.float32)
+    want = gcn_ref.softmax_rows((A.astype(np.float64) @ q.astype(np.float64)) + b[None, :])
+    for variant in (0, 1, 2):
+        got = layers.spmm(A, q, bias=b, softmax=True, variant=variant)
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-9, err_msg=str(variant))
+
+
+def test_label_and_input_caches_follow_content(problem):
+    """Fresh label vectors at a recycled address (Y[train] temporaries) and in-place edits of X must not be served from
+    stale device copies; non-canonical X (duplicate entries, unsorted rows) means what SciPy says it means."""
+    A, X, Y, tr, dev, te, cfg = problem
+    hid = [64, 64]
+    clf = _model(cfg, True, hid=hid, p=0.0)
+    clf.build_model(A, seed=2)
+    params = [p.copy() for p in clf.init_params]
+    Y2 = ((Y.astype(np.int64) * 7 + 3) % cfg["classes"]).astype(np.int32)
+    losses = []
+    for labels in (Y, Y2):
+        y_tr = labels[tr]  # temporary: the second one usually lands on the first one's address
+        losses.append(clf.f_train(X, y_tr, labels[dev], A, tr, dev, seed=1, update=False)[0])
+        del y_tr
+    r1 = gcn_ref.loss_and_grads(params, X, A, Y, tr, hid, True, None, 0.0)["train_loss"]
+    r2 = gcn_ref.loss_and_grads(params, X, A, Y2, tr, hid, True, None, 0.0)["train_loss"]
+    np.testing.assert_allclose(losses, [r1, r2], rtol=1e-3)
+    assert abs(r1 - r2) > 1e-4
+    # in-place edit without invalidate_inputs(): the content fingerprint notices
+    X2 = X.copy()
+    l0 = clf.f_train(X2, Y[tr], Y[dev], A, tr, dev, seed=1, update=False)[0]
+    X2.data *= np.float32(0.25)
+    l1 = clf.f_train(X2, Y[tr], Y[dev], A, tr, dev, seed=1, update=False)[0]
+    r = gcn_ref.loss_and_grads(params, X2, A, Y, tr, hid, True, None, 0.0)["train_loss"]
+    assert l0 != l1
+    np.testing.assert_allclose(l1, r, rtol=1e-3)
+    # duplicates and unsorted rows: X3 stores every entry twice at half weight, rows reversed
+    coo = X.tocoo()
+    order = np.argsort(-(coo.row.astype(np.int64) * X.shape[1] + coo.col), kind="stable")
+    row = np.concatenate([coo.row[order], coo.row[order]])
+    col = np.concatenate([coo.col[order], coo.col[order]])
+    val = np.concatenate([coo.data[order] * np.float32(0.5)] * 2)
+    counts = np.bincount(row, minlength=X.shape[0])
+    o2 = np.argsort(row, kind="stable")
+    indptr = np.zeros(X.shape[0] + 1, dtype=np.int32)
+    np.cumsum(counts, out=indptr[1:])
+    X3 = sp.csr_matrix((val[o2], col[o2].astype(np.int32), indptr), shape=X.shape)
+    assert not X3.has_canonical_format
+    p3, pr3 = clf.predict(X3, A, te)
+    p1, pr1 = clf.predict(X, A, te)
+    np.testing.assert_allclose(pr3, pr1, rtol=1e-5, atol=1e-9)
