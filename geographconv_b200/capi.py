@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libgcnb200.so")
 
 OK, E_INVALID, E_CUDA, E_WORKSPACE, E_UNSUPPORTED = 0, -1, -2, -3, -4
 ACT = {"linear": 0, "tanh": 1, "relu": 2, "rectify": 2, "sigmoid": 3, "selu": 4, None: 0}
-TAGS = ["spmm_a", "spmm_x", "spmm_xt", "gemm", "elementwise", "loss", "adam", "copy", "spmm_a_narrow"]
+TAGS = ["spmm_a", "spmm_x", "spmm_xt", "gemm", "elementwise", "loss", "adam", "copy", "spmm_a_narrow", "comm"]
 TAG_SPMM_A, TAG_SPMM_X, TAG_SPMM_XT, TAG_SPMM_A_NARROW = 0, 1, 2, 8
 
 
@@ -94,6 +94,16 @@ SIGNATURES = {
     "gcnb_adj_build_rows": (C.c_int, [_ctxp, _vp, _vp, _i64, _i32, _vp, _sz, _vp, C.POINTER(_i64)]),
     "gcnb_adj_fill_f32": (C.c_int, [_ctxp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "gcnb_adj_normalize_weighted_f64": (C.c_int, [_ctxp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "gcnb_peer_alloc": (C.c_int, [_ctxp, _sz, C.POINTER(_vp), _vp]),
+    "gcnb_peer_free": (C.c_int, [_ctxp, _vp]),
+    "gcnb_peer_open": (C.c_int, [_ctxp, _vp, C.POINTER(_vp)]),
+    "gcnb_peer_close": (C.c_int, [_ctxp, _vp]),
+    "gcnb_peer_setup": (C.c_int, [_ctxp, _i32, _i32, C.POINTER(_vp), _sz, _sz]),
+    "gcnb_peer_barrier": (C.c_int, [_ctxp]),
+    "gcnb_slice_push_f32": (C.c_int, [_ctxp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp]),
+    "gcnb_spmm_csr_sliced_f32": (C.c_int, [_ctxp, C.POINTER(GcnbCsr), _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32,
+                                           C.POINTER(GcnbEpilogue)]),
+    "gcnb_row_softmax_f32": (C.c_int, [_ctxp, _vp, _i32, _i32, _i32, _vp]),
 }
 
 _lib = None

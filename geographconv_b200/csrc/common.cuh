@@ -34,6 +34,13 @@ struct gcnb_ctx {
   int tc_launches = 0;
   int tc_dbg_mode = 0;
   void* tc_dbg = nullptr;  // device buffer for per-CTA phase timestamps of the highway kernel (debug tool)   // read-only: tcgen05 kernels launched so far
+  // NVLink peer memory (peer.cu): identically laid out arenas of the ranks of one box
+  char* peer_base[GCNB_MAX_PEERS] = {nullptr};
+  int peer_rank = 0;
+  int peer_world = 0;  // 0: no arena attached
+  size_t peer_bytes = 0;
+  size_t peer_flags_offset = 0;
+  int peer_timeout_s = 30;
   // profiling
   bool prof = false;
   std::vector<ProfPair> pending;
@@ -103,6 +110,9 @@ struct ProfScope {
     }
   }
 };
+
+// local arena pointer -> the same offset in rank q's arena; nullptr when [p, p + span) is not inside the local arena
+void* gcnb_peer_translate(const gcnb_ctx* ctx, const void* p, int q, size_t span);
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -60,7 +60,21 @@ struct SpmmParams {
   int k4;          // K rounded up to 4 (panel engine: the panels tile [0, k4))
   int evict_last;  // panel engine, gather cache policy: 0 default, 1 L2 evict_last hint, 2 the same with L1 allocation
   int col_base;    // panel engine: first column of panel 0 of this launch
+  // feature-sliced product of a row-partitioned run (gcnb_spmm_csr_sliced_f32): B holds this rank's column slice, the
+  // columns computed here are out_col0 + [0, k4) of the full operand, and row i of the result belongs to rank i / n_pad
+  int out_col0;
+  int n_pad;       // 0: every row is stored through C
+  float* peer_C[GCNB_MAX_PEERS];
 };
+
+// first element of output row `row`: local C, or the owning rank's copy of C in a feature-sliced product
+__device__ __forceinline__ float* out_row(const SpmmParams& p, int row) {
+  if (p.n_pad > 0) {
+    const int q = row / p.n_pad;
+    return p.peer_C[q] + (size_t)(row - q * p.n_pad) * p.ldc;
+  }
+  return p.C + (size_t)row * p.ldc;
+}
 
 constexpr int kWarpsPerCta = 8;
 
@@ -74,8 +88,10 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, floa
   for (int ch = 0; ch < NCHUNK; ++ch) {
     v[ch][0] = acc[ch].x; v[ch][1] = acc[ch].y; v[ch][2] = acc[ch].z; v[ch][3] = acc[ch].w;
   }
+  const int gcol0 = p.col0 + p.out_col0;  // first column of this pass in the full operand
+  float* const orow = out_row(p, row);
   if (p.accumulate == 2) {  // pre-activation accumulate: the product joins what C already holds (dense hot-column part)
-    const float4* crow_in = reinterpret_cast<const float4*>(p.C + (size_t)row * p.ldc + p.col0);
+    const float4* crow_in = reinterpret_cast<const float4*>(orow + gcol0);
 #pragma unroll
     for (int ch = 0; ch < NCHUNK; ++ch) {
       const int f4 = lane + 32 * ch;
@@ -90,7 +106,7 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, floa
     for (int ch = 0; ch < NCHUNK; ++ch) {
       const int f4 = lane + 32 * ch;
       if (f4 < p.nf4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + p.col0) + f4);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + gcol0) + f4);
         v[ch][0] += b.x; v[ch][1] += b.y; v[ch][2] += b.z; v[ch][3] += b.w;
       }
     }
@@ -102,17 +118,17 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, floa
         const int f4 = lane + 32 * ch;
         if (f4 < p.nf4) {
           float4 o;
-          const int c = p.col0 + 4 * f4;
+          const int c = gcol0 + 4 * f4;
           o.x = c + 0 < p.K ? v[ch][0] : 0.f; o.y = c + 1 < p.K ? v[ch][1] : 0.f;
           o.z = c + 2 < p.K ? v[ch][2] : 0.f; o.w = c + 3 < p.K ? v[ch][3] : 0.f;
-          reinterpret_cast<float4*>(p.logits + (size_t)row * p.ldc + p.col0)[f4] = o;
+          reinterpret_cast<float4*>(p.logits + (size_t)row * p.ldc + gcol0)[f4] = o;
         }
       }
     }
     float m = -INFINITY;
 #pragma unroll
     for (int ch = 0; ch < NCHUNK; ++ch) {
-      const int c = p.col0 + 4 * (lane + 32 * ch);
+      const int c = gcol0 + 4 * (lane + 32 * ch);
 #pragma unroll
       for (int e = 0; e < 4; ++e)
         if (lane + 32 * ch < p.nf4 && c + e < p.K) m = fmaxf(m, v[ch][e]);
@@ -121,7 +137,7 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, floa
     float s = 0.f;
 #pragma unroll
     for (int ch = 0; ch < NCHUNK; ++ch) {
-      const int c = p.col0 + 4 * (lane + 32 * ch);
+      const int c = gcol0 + 4 * (lane + 32 * ch);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const bool ok = lane + 32 * ch < p.nf4 && c + e < p.K;
@@ -138,7 +154,7 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, floa
 #pragma unroll
     for (int ch = 0; ch < NCHUNK; ++ch) {
       const int f4 = lane + 32 * ch;
-      const int c = p.col0 + 4 * f4;
+      const int c = gcol0 + 4 * f4;
       if (f4 < p.nf4) {
         if (p.act != GCNB_ACT_LINEAR) {
 #pragma unroll
@@ -157,7 +173,7 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, floa
       }
     }
   }
-  float4* crow = reinterpret_cast<float4*>(p.C + (size_t)row * p.ldc + p.col0);
+  float4* crow = reinterpret_cast<float4*>(orow + gcol0);
 #pragma unroll
   for (int ch = 0; ch < NCHUNK; ++ch) {
     const int f4 = lane + 32 * ch;
@@ -393,9 +409,10 @@ __device__ __forceinline__ float4 ld_gather_hint_f4(const float4* p, uint64_t po
 
 // element-wise epilogue of one float4 of an output row (no row softmax: that needs the whole row, see
 // row_softmax_kernel).  Same arithmetic, in the same order, as spmm_epilogue.
-__device__ __forceinline__ void panel_epilogue(const SpmmParams& p, int row, int c, float4 acc) {
+__device__ __forceinline__ void panel_epilogue(const SpmmParams& p, int row, int c_local, float4 acc) {
   float v[4] = {acc.x, acc.y, acc.z, acc.w};
-  float4* cptr = reinterpret_cast<float4*>(p.C + (size_t)row * p.ldc + c);
+  const int c = c_local + p.out_col0;  // column in the full operand (bias, padding rule, dropout counter, store)
+  float4* cptr = reinterpret_cast<float4*>(out_row(p, row) + c);
   if (p.accumulate == 2) {
     const float4 o = *cptr;
     v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
@@ -898,5 +915,83 @@ extern "C" int gcnb_spmm_csr_f32(gcnb_ctx* ctx, const gcnb_csr* A, const float* 
     row_softmax_wide_kernel<<<cdiv(A->n_rows, kWarpsPerCta), kWarpsPerCta * 32, 0, ctx->stream>>>(p, A->n_rows);
     GCNB_LAUNCHED(ctx);
   }
+  return GCNB_OK;
+}
+
+// C[:, col0 : col0 + width] = epilogue(A . XP[:, 0 : width]) over all rows of the replicated A_hat; row i lands in rank
+// (i / n_pad)'s copy of C (peer memory, csrc/peer.cu).  Always the panel engine: its lane groups own (row item, column
+// panel) pairs, so a column slice is simply fewer panels, and every row is still summed in CSR order by one group.
+extern "C" int gcnb_spmm_csr_sliced_f32(gcnb_ctx* ctx, const gcnb_csr* A, const float* XP, int32_t ldp, float* C,
+                                        int32_t ldc, int32_t K, int32_t col0, int32_t width, int32_t n_pad,
+                                        const gcnb_epilogue* epi) {
+  if (!ctx) return GCNB_E_INVALID;
+  GCNB_REQUIRE(ctx, ctx->peer_world >= 2, "no peer arena attached (gcnb_peer_setup)");
+  GCNB_REQUIRE(ctx, A && XP && C, "null matrix");
+  GCNB_REQUIRE(ctx, K > 0 && col0 >= 0 && width >= 0 && n_pad > 0, "bad slice");
+  GCNB_REQUIRE(ctx, col0 % 4 == 0 && width % 4 == 0 && ldp % 4 == 0 && ldc % 4 == 0 && ldp >= width && col0 + width <= ldc,
+               "slice: columns in multiples of 4 inside C");
+  GCNB_REQUIRE(ctx, aligned16(XP) && aligned16(C), "XP and C must be 16-byte aligned");
+  GCNB_REQUIRE(ctx, (long long)n_pad * ctx->peer_world >= A->n_rows, "n_pad * world must cover the rows of A");
+  GCNB_REQUIRE(ctx, A->n_rows == 0 || (A->items && A->rowptr), "CSR not planned");
+  GCNB_REQUIRE(ctx, A->nnz == 0 || (A->colidx && A->val), "CSR arrays missing");
+  GCNB_REQUIRE(ctx, A->n_long == 0 || A->long_rows, "long row table missing");
+  if (epi) {
+    GCNB_REQUIRE(ctx, !epi->softmax && epi->accumulate == 0 && epi->dropout_p == 0.f && !epi->logits,
+                 "sliced product: bias + activation epilogue only");
+    GCNB_REQUIRE(ctx, !epi->bias || aligned16(epi->bias), "bias must be 16-byte aligned");
+  }
+  if (A->n_rows == 0 || width == 0) return GCNB_OK;
+  if (A->n_slots > 0) {
+    const size_t need = gcnb_spmm_workspace_bytes(A, width);
+    if (!ctx->ws || ctx->ws_bytes < need)
+      return gcnb_fail(ctx, GCNB_E_WORKSPACE, "spmm needs %s%lld workspace bytes, have %lld", "", (long long)need,
+                       (long long)ctx->ws_bytes);
+  }
+  ProfScope scope(ctx, A->tag >= 0 && A->tag < GCNB_NTAGS ? A->tag : GCNB_TAG_SPMM_A);
+  SpmmParams p;
+  memset(&p, 0, sizeof(p));
+  p.items = reinterpret_cast<const int4*>(A->items);
+  p.n_items = A->n_items;
+  p.col = A->colidx;
+  p.val = A->val;
+  p.B = XP; p.ldb = ldp; p.C = C; p.ldc = ldc; p.K = K;
+  p.counter = reinterpret_cast<int*>(ctx->ws);
+  p.partial = ctx->ws ? reinterpret_cast<float*>(reinterpret_cast<char*>(ctx->ws) + 256) : nullptr;
+  p.long_rows = A->long_rows;
+  p.n_long = A->n_long;
+  p.out_col0 = col0;
+  p.n_pad = n_pad;
+  const size_t span = ((size_t)n_pad - 1) * (size_t)ldc * sizeof(float) + (size_t)(col0 + width) * sizeof(float);
+  for (int q = 0; q < ctx->peer_world; ++q) {
+    p.peer_C[q] = reinterpret_cast<float*>(gcnb_peer_translate(ctx, C, q, span));
+    GCNB_REQUIRE(ctx, p.peer_C[q] != nullptr, "C is not inside the peer arena");
+  }
+  if (epi) {
+    p.bias = epi->bias; p.act = epi->act;
+  }
+  return launch_panels(ctx, p, A->n_rows, width, ctx->spmm_unroll, true);
+}
+
+extern "C" int gcnb_row_softmax_f32(gcnb_ctx* ctx, float* C, int32_t ldc, int32_t n_rows, int32_t K, float* logits) {
+  if (!ctx) return GCNB_E_INVALID;
+  GCNB_REQUIRE(ctx, C && K > 0 && n_rows >= 0, "bad argument");
+  const int K4 = ((K + 3) / 4) * 4;
+  GCNB_REQUIRE(ctx, ldc % 4 == 0 && ldc >= K4 && aligned16(C) && (!logits || aligned16(logits)), "ldc / alignment");
+  if (n_rows == 0) return GCNB_OK;
+  ProfScope scope(ctx, GCNB_TAG_LOSS);
+  SpmmParams p;
+  memset(&p, 0, sizeof(p));
+  p.C = C; p.ldc = ldc; p.K = K; p.k4 = K4; p.nf4 = K4 / 4; p.softmax = 1; p.logits = logits;
+  if (K4 > kMaxPassCols) {
+    row_softmax_wide_kernel<<<cdiv(n_rows, kWarpsPerCta), kWarpsPerCta * 32, 0, ctx->stream>>>(p, n_rows);
+  } else {
+    switch ((p.nf4 + 31) / 32) {
+      case 1: launch_softmax<1>(ctx, p, n_rows); break;
+      case 2: launch_softmax<2>(ctx, p, n_rows); break;
+      case 3: launch_softmax<3>(ctx, p, n_rows); break;
+      default: launch_softmax<4>(ctx, p, n_rows); break;
+    }
+  }
+  GCNB_LAUNCHED(ctx);
   return GCNB_OK;
 }

@@ -22,8 +22,18 @@ Layer arithmetic, per SURVEY.md 8a:
 * output layer     P = softmax(A.(x.Wout) + bout)                      (gcnmodel.py:149-157)
 
 Row-partitioned runs (world > 1): rank p owns the contiguous row block
-[p*n_pad, (p+1)*n_pad) of A, X and every activation; before each A-SpMM the dense operand is
-all-gathered (NCCL over NVLink), weight gradients are all-reduced once per step.
+[p*n_pad, (p+1)*n_pad) of X and of every activation; weights are replicated and their gradients
+all-reduced once per step (NCCL).  A graph convolution needs rows of the dense operand that live on
+other ranks; two exchange designs are built in (``GCNB_EXCHANGE``):
+
+* ``slice`` (default): A_hat is replicated (nnz*8 bytes), rank q multiplies ALL rows of A_hat by ITS
+  column slice of the operand; the transposes before and after the product are stores into the
+  peers' memory over NVLink (csrc/peer.cu).  N*K*4*(P-1)/P^2 bytes per rank each way.
+* ``gather``: rank p keeps its row block of A_hat and all-gathers the whole N x K operand (NCCL).
+  N*K*4*(P-1)/P bytes into every rank -- the round-1 design, kept for comparison and as the path
+  when CUDA IPC is unavailable.
+
+Both sum every row in CSR order, so the forward pass is bit-identical to the single-GPU one.
 """
 from __future__ import annotations
 
@@ -36,7 +46,8 @@ import torch
 
 from . import capi
 from .capi import ACT, GcnbCsr, GcnbEpilogue
-from .partition import ParamLayout, ld_of, local_index_split, row_blocks, slice_rows, transpose_csr, is_symmetric
+from .partition import (ParamLayout, ld_of, local_index_split, row_blocks, slice_columns, slice_rows, transpose_csr,
+                        is_symmetric)
 
 SPMM_CHUNK_DEFAULT = 1024  # nonzeros per row item (rows longer than this are split; see gcnb_csr_plan)
 
@@ -218,7 +229,7 @@ class HostGraph:
     memory across epochs, gcnmain.py:172-179) and cached by the engine."""
 
     def __init__(self, X, A, world, rank, chunk, need_backward, assume_symmetric=None, hot_density=0.0,
-                 hot_max=0, xt_blocks=0, allreduce=None):
+                 hot_max=0, xt_blocks=0, allreduce=None, full_graph=False):
         n = X.shape[0]
         self.n = n
         self.n_pad, blocks = row_blocks(n, world)
@@ -232,7 +243,10 @@ class HostGraph:
                 return sp.csr_matrix((M.data, M.indices, M.indptr), shape=(M.shape[0], self.n_tot))
             return M
 
-        if world > 1:
+        self.full_graph = bool(full_graph) and world > 1
+        if self.full_graph:      # feature-sliced exchange: every rank multiplies all rows of A_hat
+            Xl, Al = slice_rows(X, self.r0, self.r1), A.tocsr()
+        elif world > 1:
             Xl, Al = slice_rows(X, self.r0, self.r1), widen(slice_rows(A, self.r0, self.r1))
         else:
             Xl, Al = X.tocsr(), A.tocsr()
@@ -259,7 +273,7 @@ class HostGraph:
             if not self.symmetric:
                 # A^T.G for a row block needs rows r0:r1 of A^T
                 AT = transpose_csr(A)
-                ATl = widen(slice_rows(AT, self.r0, self.r1)) if world > 1 else AT
+                ATl = AT if (world == 1 or self.full_graph) else widen(slice_rows(AT, self.r0, self.r1))
                 self.AT = HostCsr(ATl, chunk)
         self.nbytes = sum(c.nbytes for c in (self.X, self.XT, self.A, self.AT) if c is not None)
         if self.kh:
@@ -319,6 +333,106 @@ class DeviceCsr:
         return self.nnz * 8 + (self.shape[0] + 1) * 4 + self.nnz * K * 4 + self.shape[0] * K * 4
 
 
+class PeerUnavailable(RuntimeError):
+    """CUDA IPC peer memory could not be set up on every rank (the engine then uses the all-gather exchange)."""
+
+
+class _RawDeviceArray:
+    """``__cuda_array_interface__`` holder: lets torch view memory the library allocated (the IPC arena)."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+        self._owner = owner
+
+
+class PeerArena:
+    """One rank's arena of NVLink peer memory (csrc/peer.cu): ``gcnb_peer_alloc`` + IPC handle exchange + ``gcnb_peer_open``
+    of every peer's arena + ``gcnb_peer_setup``.  All ranks must create arenas of the same size in the same order and
+    carve them identically (the engine does: identical buffer plans), so that equal offsets mean equal buffers.
+    Collective: every rank of ``eng.group`` must call it together."""
+
+    FLAG_BYTES = 256
+
+    def __init__(self, eng, nbytes):
+        import torch.distributed as dist
+        # no reference to the engine itself (it owns this arena: a cycle would keep both alive until a gc pass)
+        self.ctx, self.dev, self.rank, self.world = eng.ctx, eng.dev, eng.rank, eng.world
+        group = eng.group
+        eng = None
+        self.nbytes = int(-(-(int(nbytes) + self.FLAG_BYTES + 4096) // 4096) * 4096)
+        self.ptr = C.c_void_p()
+        self.peers = []
+        self.off = self.FLAG_BYTES
+        handle = (C.c_ubyte * 64)()
+        ok = 1
+        try:
+            self.ctx.call("gcnb_peer_alloc", self.nbytes, C.byref(self.ptr), handle)
+        except capi.GcnbError as e:
+            self.err = str(e)
+            ok = 0
+        # sizes must agree on every rank, and every rank must have its memory
+        info = torch.tensor([ok, -ok, self.nbytes, -self.nbytes], dtype=torch.int64, device=self.dev)
+        dist.all_reduce(info, op=dist.ReduceOp.MIN, group=group)
+        info = info.tolist()
+        if info[0] == 0 or info[2] != -info[3]:
+            self._free_local()
+            raise PeerUnavailable("peer arena: allocation failed on a rank or sizes differ (%s)" % getattr(self, "err", info))
+        mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=self.dev)
+        allh = torch.empty(64 * self.world, dtype=torch.uint8, device=self.dev)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        allh = bytes(allh.cpu().numpy().tobytes())
+        bases = []
+        ok = 1
+        for q in range(self.world):
+            if q == self.rank:
+                bases.append(self.ptr.value)
+                continue
+            pp = C.c_void_p()
+            buf = (C.c_ubyte * 64).from_buffer_copy(allh[64 * q:64 * q + 64])
+            try:
+                self.ctx.call("gcnb_peer_open", buf, C.byref(pp))
+                self.peers.append(pp)
+                bases.append(pp.value)
+            except capi.GcnbError as e:
+                self.err = str(e)
+                ok = 0
+                break
+        flag = torch.tensor([ok], dtype=torch.int64, device=self.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            self.close()
+            raise PeerUnavailable("peer arena: cudaIpcOpenMemHandle failed on a rank (%s)" % getattr(self, "err", ""))
+        table = (C.c_void_p * self.world)(*bases)
+        self.ctx.call("gcnb_peer_setup", self.rank, self.world, table, self.nbytes, 0)
+        dist.barrier(group=group)  # every rank's flag block is zeroed and registered before the first device barrier
+
+    def take(self, rows, ld, dtype=torch.float32):
+        """Carve a zero-filled (rows x ld) fp32 matrix (256-byte aligned) out of the arena as a torch view."""
+        nbytes = int(rows) * int(ld) * 4
+        off = self.off
+        self.off = -(-(off + nbytes) // 256) * 256
+        if self.off > self.nbytes:
+            raise capi.GcnbError("peer arena exhausted: %d of %d bytes" % (self.off, self.nbytes))
+        holder = _RawDeviceArray(self.ptr.value + off, (int(rows), int(ld)), "<f4", self)
+        return torch.as_tensor(holder, device=self.dev)
+
+    def _free_local(self):
+        if self.ptr.value:
+            self.self.ctx.call("gcnb_peer_free", self.ptr)
+            self.ptr = C.c_void_p()
+
+    def close(self):
+        """Collective in spirit: every rank unmaps its peers before any rank frees (callers barrier around it)."""
+        try:
+            self.self.ctx.call("gcnb_peer_setup", 0, 0, None, 0, 0)
+            for pp in self.peers:
+                self.self.ctx.call("gcnb_peer_close", pp)
+            self.peers = []
+        finally:
+            self._free_local()
+
+
 class Engine:
     """One GPU's share of the GCN: weights (replicated), row block of the graph, activations."""
 
@@ -366,6 +480,29 @@ class Engine:
         self.copy_stream = torch.cuda.Stream(self.dev)
         self.copy_ctx = capi.Context(int(device), C.c_void_p(self.copy_stream.cuda_stream))
         self._uploads = {}
+        # exchange design of the graph convolutions (module docstring); "slice" needs CUDA IPC between the ranks
+        self.exchange = os.environ.get("GCNB_EXCHANGE", "slice") if self.world > 1 else "none"
+        if self.exchange not in ("slice", "gather", "none"):
+            raise ValueError("GCNB_EXCHANGE must be 'slice' or 'gather'")
+        self.arena = None
+        self._slice_plans = {}
+        if self.world > 1 and "GCNB_PEER_TIMEOUT_S" in os.environ:
+            self.ctx.set_option("peer_timeout_s", int(os.environ["GCNB_PEER_TIMEOUT_S"]))
+        if self.exchange == "slice":
+            if self.world > 16:
+                self.exchange = "gather"
+            else:
+                try:  # probe once: a tiny arena, mapped by every peer, one device barrier
+                    probe = PeerArena(self, 1 << 16)
+                    self.ctx.call("gcnb_peer_barrier")
+                    self.ctx.sync()
+                    torch.distributed.barrier(group=self.group)
+                    probe.close()
+                    torch.distributed.barrier(group=self.group)
+                except PeerUnavailable as e:
+                    import logging
+                    logging.warning("NVLink peer memory unavailable (%s): using the all-gather exchange", e)
+                    self.exchange = "gather"
         if self.world > 1 and "GCNB_SM_MARGIN" in os.environ:
             # SMs the persistent SpMM kernel leaves to concurrently running NCCL kernels
             self.ctx.set_option("sm_margin", int(os.environ["GCNB_SM_MARGIN"]))
@@ -382,6 +519,8 @@ class Engine:
         self.metrics_host = torch.zeros(8, dtype=torch.float32).pin_memory()
         self._fence()
         self.ws = None
+        self._measuring = False
+        self._measured = 0
         self._keepalive = []
         self.n = None  # rows bound (global)
         self.A = self.X = self.XT = self.AT = None
@@ -427,7 +566,34 @@ class Engine:
         return C.c_void_p(self.grads.data_ptr() + 4 * e["offset"]), e["ld"]
 
     def _zeros(self, rows, ld):
-        return torch.zeros((max(rows, 1), ld), dtype=torch.float32, device=self.dev)
+        rows = max(int(rows), 1)
+        if self._measuring:  # sizing pass of _alloc_buffers: count what the arena must hold
+            self._measured += -(-(rows * int(ld) * 4) // 256) * 256
+            return None
+        if self.arena is not None:
+            return self.arena.take(rows, ld)
+        return torch.zeros((rows, ld), dtype=torch.float32, device=self.dev)
+
+    def _release_arena(self):
+        if self.arena is not None:
+            self.ctx.sync()
+            torch.distributed.barrier(group=self.group)  # nobody is still storing into a peer
+            self.arena.close()
+            torch.distributed.barrier(group=self.group)
+            self.arena = None
+
+    def close(self):
+        """Release the peer arena (collective when world > 1).  Called by __del__ as a last resort."""
+        try:
+            if self.arena is not None:
+                self.ctx.sync()
+                self.arena.close()
+                self.arena = None
+        except Exception:
+            pass
+
+    def __del__(self):
+        self.close()
 
     def _fence(self):
         """Order torch-side fills (current stream) before engine-stream kernels that use the buffers."""
@@ -477,7 +643,8 @@ class Engine:
             self.copy_ctx.sync()
             self._uploads = {}
             hg = HostGraph(X, A, self.world, self.rank, self.spmm_chunk, need_backward, assume_symmetric,
-                           self.hot_density, self.hot_max, self.xt_blocks, allreduce=self._allreduce_host)
+                           self.hot_density, self.hot_max, self.xt_blocks, allreduce=self._allreduce_host,
+                           full_graph=self.exchange == "slice")
             self.host = hg
             self._bound_refs = (X, A)
             self.n, self.n_pad, self.r0, self.r1 = hg.n, hg.n_pad, hg.r0, hg.r1
@@ -549,6 +716,25 @@ class Engine:
                 self.stream.wait_event(ev)
 
     def _alloc_buffers(self, need_backward):
+        if self.exchange == "slice":
+            # every dense buffer of the step lives in the NVLink peer arena (peers store result rows and operand slices
+            # straight into them); sizing pass first, then the arena, then the real carve -- identical on every rank
+            self._release_arena()
+            self.lay = []  # drop views of the old arena
+            self._measuring, self._measured = True, 0
+            self._alloc_buffers_impl(need_backward)
+            self._measuring = False
+            self.arena = PeerArena(self, self._measured + (1 << 20))
+        self._alloc_buffers_impl(need_backward)
+
+    def _slice_plan(self, K):
+        """(col0, width, ldp) int32 arrays of the feature-sliced product at operand width K (partition.slice_columns)."""
+        pl = self._slice_plans.get(int(K))
+        if pl is None:
+            pl = self._slice_plans[int(K)] = slice_columns(int(K), self.world)
+        return pl
+
+    def _alloc_buffers_impl(self, need_backward):
         L = self.layout
         n = self.n_pad if self.world > 1 else self.n_loc
         hd = L.hid[0]
@@ -568,8 +754,12 @@ class Engine:
         self.S = self._zeros(n, maxld)  # A.x scratch (highway) / x.W scratch (plain, output)
         self.P = self._zeros(n, self.ldc)
         self.logits = self._zeros(n, self.ldc) if self.keep_logits else None
-        self.gath = self.pack = None
-        if self.world > 1:
+        self.gath = self.pack = self.XP = None
+        if self.exchange == "slice":
+            # panel buffer: this rank's column slice of the operand, all rows (peers push their row blocks into it)
+            ldp_max = max(int(self._slice_plan(w)[2].max()) for w in set(widths + [L.output_size]))
+            self.XP = self._zeros(self.n_tot, ldp_max)
+        elif self.world > 1:
             self.gath = self._zeros(self.n_tot, maxld)   # gathered panels, laid out one after the other
             self.pack = self._zeros(n, maxld)            # this rank's panels made contiguous for the collective
         if need_backward:
@@ -593,6 +783,8 @@ class Engine:
             need = max(need, self.lib.gcnb_gemm_workspace_bytes(0, max(n, 1), hd, self.kh))
             if need_backward:
                 need = max(need, self.lib.gcnb_gemm_workspace_bytes(1, self.kh, hd, max(n, 1)))
+        if self._measuring:
+            return
         if need_backward:
             need = max(need, self.lib.gcnb_spmm_workspace_bytes(C.byref(self.XT.struct), hd))
             wmax = max(widths + [L.output_size])
@@ -663,10 +855,16 @@ class Engine:
         return [(c0, min(w, ld - c0), min(K - c0, min(w, ld - c0))) for c0 in range(0, ld, w) if c0 < K]
 
     def _conv_begin(self, x, K, whole=False):
-        """Start moving the dense operand ``x`` (n_pad x ld, this rank's rows) of a graph convolution to every rank:
-        one all-gather per column panel on the side stream.  No-op on a single GPU."""
+        """Start moving the dense operand ``x`` (n_pad x ld, this rank's rows) of a graph convolution to the ranks that
+        need it.  No-op on a single GPU.  ``slice``: push this rank's rows of every column slice into the owners' panel
+        buffers (NVLink stores).  ``gather``: one all-gather per column panel on the side stream."""
         if self.world == 1:
             return x
+        if self.exchange == "slice":
+            col0, width, ldp = self._slice_plan(K)
+            self.ctx.call("gcnb_slice_push_f32", _ptr(x), int(x.shape[1]), self.n_loc, int(self.r0), _ptr(self.XP),
+                          C.c_void_p(col0.ctypes.data), C.c_void_p(width.ctypes.data), C.c_void_p(ldp.ctypes.data))
+            return ("slice", int(K))
         ld = x.shape[1]
         panels = self._panels(K, ld, whole)
         srcs = []
@@ -700,6 +898,20 @@ class Engine:
             x = handle
             self._spmm(csr, x, x.shape[1], out, ldo, K, bias=bias, act=act, softmax=softmax, logits=logits)
             return
+        if self.exchange == "slice":
+            col0, width, ldp = self._slice_plan(K)
+            q = self.rank
+            epi = GcnbEpilogue()
+            epi.bias = bias.value if isinstance(bias, C.c_void_p) else bias
+            epi.act = int(act)
+            self.ctx.call("gcnb_peer_barrier")  # every rank's rows of my slice have landed in XP
+            self.ctx.call("gcnb_spmm_csr_sliced_f32", C.byref(csr.struct), _ptr(self.XP), int(ldp[q]), _ptr(out), int(ldo),
+                          int(K), int(col0[q]), int(width[q]), int(self.n_pad), C.byref(epi))
+            self.ctx.call("gcnb_peer_barrier")  # every rank's columns of my rows have landed in `out`
+            if softmax:
+                self.ctx.call("gcnb_row_softmax_f32", _ptr(out), int(ldo), self.n_loc, int(K),
+                              _ptr(logits) if logits is not None else None)
+            return
         for dst, ev, c0, w, kc in handle:
             self.stream.wait_event(ev)
             b = None if bias is None else C.c_void_p(bias.value + 4 * c0)
@@ -711,8 +923,24 @@ class Engine:
         self._conv_finish(self._conv_begin(x, K, whole), csr, out, ldo, K, **epi)
 
     def conv_touched_bytes(self, K):
-        """B_touch of one A_hat . H product of this rank."""
+        """B_touch of one A_hat . H product of this rank: all columns of its rows, or -- feature-sliced --
+        its column slice of all rows."""
+        if self.exchange == "slice":
+            w = int(self._slice_plan(K)[1][self.rank])
+            return self.A.nnz * 8 + (self.A.shape[0] + 1) * 4 + self.A.nnz * w * 4 + self.A.shape[0] * w * 4
         return self.A.touched_bytes(K)
+
+    def conv_exchange_bytes(self, K):
+        """Bytes this rank sends over NVLink for one graph convolution at operand width K."""
+        if self.world == 1:
+            return 0
+        k4 = (int(K) + 3) // 4 * 4
+        if self.exchange == "slice":
+            col0, width, _ = self._slice_plan(K)
+            push = self.n_loc * (k4 - int(width[self.rank])) * 4
+            back = (self.n - self.n_loc) * int(width[self.rank]) * 4
+            return push + back
+        return self.n_pad * ld_of(K) * 4 * (self.world - 1)
 
     # ------------------------------------------------------------------ forward
     def forward(self, train=False, seed=0, want_gates=False):
@@ -810,11 +1038,12 @@ class Engine:
                 Wt, ldwt = self._pptr("Wt%d" % k)
                 # everything that does not need V = A^T.dHpre runs while its operand is being exchanged
                 self._gemm(1, 0, n_in, n_out, n, xin, ldin, dT, ldy, gWt, ldgt)     # dWt = x^T.dTpre
-                if self.world > 1:  # keeps the exchange of dHpre covered
+                split_dgrad = self.exchange == "gather"  # a GEMM of its own keeps the all-gather of dHpre covered
+                if split_dgrad:
                     self._gemm(0, 1, n, n_in, n_out, dT, ldy, Wt, ldwt, dX, ldin, accumulate=1)  # dx += dTpre.Wt^T
                 self._conv_finish(pending, csrT, V, ldy, n_out)                     # V = A^T.dHpre
                 self._gemm(1, 0, n_in, n_out, n, xin, ldin, V, ldy, gWh, ldgh)      # dWh = x^T.V
-                if self.world > 1:
+                if split_dgrad:
                     self._gemm(0, 1, n, n_in, n_out, V, ldy, Wh, ldwh, dX, ldin, accumulate=1)   # dx += V.Wh^T
                 elif n > 0:  # one pass over dx: dx += dTpre.Wt^T + V.Wh^T
                     self.ctx.call("gcnb_gemm_pair_f32", 1, n, n_in, n_out, _ptr(dT), ldy, Wt, ldwt, _ptr(V), ldy, Wh,

@@ -131,6 +131,15 @@ class GraphConv():
             self._engine.set_params(self._host_params)
         return self._engine
 
+    def close(self):
+        """Release the device engine (HBM buffers, NVLink peer arena).  Collective when the graph is sharded over
+        several GPUs: every rank calls it at the same point.  The model can still be used afterwards (a new engine
+        is created on demand from the host copy of the weights)."""
+        if self._engine is not None:
+            self._host_params = self._engine.get_params()
+            self._engine.close()
+            self._engine = None
+
     def invalidate_inputs(self):
         """Forget the prepared copies of X / A (pinned host staging + device CSR).  They are keyed on the identity,
         shape and nnz of the SciPy objects, so a matrix edited IN PLACE between calls needs this; new objects are

@@ -122,6 +122,31 @@ def row_blocks(n, world):
     return n_pad, [(min(n, p * n_pad), min(n, (p + 1) * n_pad)) for p in range(world)]
 
 
+SLICE_UNIT = 16  # floats: column slices are cut at multiples of 16 columns (one 4-lane group of the panel SpMM)
+
+
+def slice_columns(K, world):
+    """Column slices of a K-wide dense operand for the feature-sliced graph convolution (csrc/peer.cu):
+    rank q multiplies all rows of A_hat by columns [col0[q], col0[q] + width[q]).  Slices are runs of 16-column units,
+    as even as possible (the first K/16 mod world ranks get one more), the last one is cut at K rounded up to 4.
+    ldp[q] = leading dimension of q's panel buffer (its slice rounded up to 32 floats: rows start on 128-byte lines).
+    K = 300 on 8 ranks: 19 units -> widths 48, 48, 48, 32, 32, 32, 32, 28; on 2 ranks 160 + 140.
+    Returns three int32 arrays of ``world`` entries."""
+    k4 = round_up(K, 4)
+    units = (k4 + SLICE_UNIT - 1) // SLICE_UNIT
+    base, extra = divmod(units, world)
+    col0 = np.zeros(world, dtype=np.int32)
+    width = np.zeros(world, dtype=np.int32)
+    c = 0
+    for q in range(world):
+        u = base + (1 if q < extra else 0)
+        col0[q] = min(c, k4)
+        width[q] = max(0, min(u * SLICE_UNIT, k4 - c))
+        c += u * SLICE_UNIT
+    ldp = np.array([round_up(max(int(w), 4), LD_ALIGN) for w in width], dtype=np.int32)
+    return col0, width, ldp
+
+
 def slice_rows(M, r0, r1):
     M = M.tocsr()
     out = M[r0:r1]

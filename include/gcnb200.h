@@ -56,7 +56,8 @@ enum gcnb_tag {
   GCNB_TAG_ADAM = 6,    /* lasagne.updates.adam (gcnmodel.py:407) */
   GCNB_TAG_COPY = 7,    /* host<->device copies issued through this ABI */
   GCNB_TAG_SPMM_A_NARROW = 8, /* A_hat . (x Wout) and its gradient: K = classes, not the hidden width */
-  GCNB_NTAGS = 9
+  GCNB_TAG_COMM = 9,    /* multi-GPU exchange kernels of this library: slice pushes and peer barriers */
+  GCNB_NTAGS = 10
 };
 
 /* ---------------------------------------------------------------- context ------------- */
@@ -272,6 +273,49 @@ int gcnb_adj_build_rows(gcnb_ctx* ctx, const int32_t* u, const int32_t* v, int64
                         void* work, size_t work_bytes, int32_t* rowptr, int64_t* nnz_host);
 int gcnb_adj_fill_f32(gcnb_ctx* ctx, int64_t n_edges, int32_t n_nodes, const void* work, const int32_t* rowptr,
                       int32_t* colidx, float* val);
+
+/* ---------------------------------------------------------------- multi-GPU exchange -- */
+/* Row-partitioned runs on one NVSwitch box (the reference is single-process, gcnmodel.py:429-430).
+ * Every rank (one process per GPU) owns an identically laid out ARENA of device memory that its peers map through
+ * CUDA IPC; a graph convolution then runs feature-sliced: A_hat is replicated, rank q multiplies all rows of A_hat
+ * by ITS column slice of the dense operand, and the two transposes around that product are stores into peer
+ * memory (csrc/peer.cu).  Per rank and product N*K*4*(P-1)/P^2 bytes cross NVLink each way, against N*K*4*(P-1)/P
+ * for an all-gather of the operand.
+ *
+ * The arena is the one allocation the library makes itself (allocator blocks cannot be exported through IPC):
+ *   gcnb_peer_alloc  cudaMalloc + zero fill + IPC handle (GCNB_IPC_HANDLE_BYTES bytes, to be sent to the peers)
+ *   gcnb_peer_open   map a peer's handle; gcnb_peer_close / gcnb_peer_free undo the two
+ *   gcnb_peer_setup  register {base address of every rank's arena as mapped HERE, own rank included}, the arena
+ *                    size and the offset of a GCNB_PEER_FLAG_BYTES flag block (zeroed) used by the barrier;
+ *                    world == 0 detaches. */
+#define GCNB_MAX_PEERS 16
+#define GCNB_IPC_HANDLE_BYTES 64
+#define GCNB_PEER_FLAG_BYTES 256
+int gcnb_peer_alloc(gcnb_ctx* ctx, size_t bytes, void** dev_ptr, void* handle_out);
+int gcnb_peer_free(gcnb_ctx* ctx, void* dev_ptr);
+int gcnb_peer_open(gcnb_ctx* ctx, const void* handle, void** peer_ptr);
+int gcnb_peer_close(gcnb_ctx* ctx, void* peer_ptr);
+int gcnb_peer_setup(gcnb_ctx* ctx, int32_t rank, int32_t world, void* const* arena_base, size_t arena_bytes,
+                    size_t flags_offset);
+/* All ranks' streams meet: returns (on the stream) once every rank has launched the same barrier and everything
+ * the ranks stored into peer memory before it is visible.  A rank that never arrives trips "peer_timeout_s"
+ * (option, default 30) and the kernel traps. */
+int gcnb_peer_barrier(gcnb_ctx* ctx);
+/* rows -> column slices: copy x[0:n_loc, col0[q] : col0[q] + width[q]] (this rank's rows, global row0 + r) into rank
+ * q's panel buffer at rows row0 + r, for every q (own rank included).  `xp_local` is THIS rank's address of the
+ * panel buffer inside the arena (peers' addresses follow from the arena bases); ldp[q] is the leading dimension of
+ * q's panel buffer.  col0 / width / ldp: host arrays of world entries, multiples of 4. */
+int gcnb_slice_push_f32(gcnb_ctx* ctx, const float* x, int32_t ldx, int32_t n_loc, int64_t row0, float* xp_local,
+                        const int32_t* col0, const int32_t* width, const int32_t* ldp);
+/* The sliced product: C[:, col0 : col0 + width] = epilogue(A . XP[:, 0 : width]) for ALL rows of A (the replicated
+ * A_hat, n_rows = N); row i is stored into rank (i / n_pad)'s copy of C at local row i % n_pad.  `C` is this rank's
+ * address of the output inside the arena (ldc floats per row, K = logical width of the whole operand for the
+ * zero-padding rule), `bias` is indexed by the global column.  Epilogue: bias + activation only.  structured_dot(A, .)
+ * of gcnmodel.py:130,153 and its gradient, each row summed in CSR order exactly as in gcnb_spmm_csr_f32. */
+int gcnb_spmm_csr_sliced_f32(gcnb_ctx* ctx, const gcnb_csr* A, const float* XP, int32_t ldp, float* C, int32_t ldc,
+                             int32_t K, int32_t col0, int32_t width, int32_t n_pad, const gcnb_epilogue* epi);
+/* row softmax in place over C[n_rows x K] (after a sliced product + bias has landed); optional copy of the logits */
+int gcnb_row_softmax_f32(gcnb_ctx* ctx, float* C, int32_t ldc, int32_t n_rows, int32_t K, float* logits);
 
 /* Weighted graphs (nx.adjacency_matrix(..., weight='w'), gcnmain.py:115): `rowptr` / `colidx` / `weights` (device,
  * float64 like the SciPy matrix networkx returns) hold the symmetric weighted adjacency with its unit diagonal

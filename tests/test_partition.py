@@ -119,6 +119,106 @@ def test_row_partitioned_exchange_world2_gloo():
         assert abs(loss - want_loss) < 1e-4
 
 
+def _p2p_exchange(dist, torch, send_blocks, recv_shapes, rank, world):
+    """What the NVLink stores of csrc/peer.cu do, with gloo send/recv: block q of ``send_blocks`` lands on rank q."""
+    recv = [torch.empty(sh, dtype=torch.float32) for sh in recv_shapes]
+    recv[rank].copy_(torch.from_numpy(np.ascontiguousarray(send_blocks[rank])))
+    reqs = []
+    for q in range(world):
+        if q != rank:
+            reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(send_blocks[q])), dst=q))
+            reqs.append(dist.irecv(recv[q], src=q))
+    for r in reqs:
+        r.wait()
+    return [t.numpy() for t in recv]
+
+
+def _rank_main_sliced(rank, world, port, q):
+    """Feature-sliced graph convolution on CPU with the engine's exchange pattern (partition.slice_columns): push row
+    blocks of every column slice to its owner, multiply ALL rows of A by the slice, send result rows home."""
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        A, X, Y, tr, dev, te, cfg = synth.synthetic_problem(dict(n=103, deg=5, f=40, xnnz=6, hid=[44, 44, 44], classes=5))
+        params = gcn_ref.init_params(cfg["f"], cfg["hid"], cfg["classes"], True, 3)
+        n = cfg["n"]
+        n_pad, blocks = partition.row_blocks(n, world)
+        r0, r1 = blocks[rank]
+        Xl = partition.slice_rows(X, r0, r1)
+
+        def conv(x):  # x: this rank's rows (r1 - r0) x K  ->  (A . x_all)[r0:r1]
+            K = x.shape[1]
+            col0, width, _ = partition.slice_columns(K, world)
+            k4 = partition.round_up(K, 4)
+            xpad = np.zeros((r1 - r0, k4), dtype=np.float32)
+            xpad[:, :K] = x
+            # push: my rows of slice q -> rank q
+            send = [xpad[:, col0[p]:col0[p] + width[p]] for p in range(world)]
+            shapes = [(blocks[p][1] - blocks[p][0], int(width[rank])) for p in range(world)]
+            XP = np.concatenate(_p2p_exchange(dist, torch, send, shapes, rank, world), axis=0)   # all rows, my slice
+            part = np.asarray(A @ XP, dtype=np.float32) if width[rank] else np.zeros((n, 0), np.float32)
+            # result rows go home: rows of rank p, my columns -> rank p
+            send = [part[blocks[p][0]:blocks[p][1]] for p in range(world)]
+            shapes = [(r1 - r0, int(width[p])) for p in range(world)]
+            cols = _p2p_exchange(dist, torch, send, shapes, rank, world)
+            return np.concatenate(cols, axis=1)[:, :K]
+
+        W0, b0 = params[0], params[1]
+        x = np.tanh(Xl @ W0 + b0)
+        first_conv = conv(x)
+        k = 2
+        for _ in range(2):
+            Wt, bt, Wh, bh = params[k:k + 4]
+            k += 4
+            h = np.tanh(conv(x) @ Wh + bh)
+            t = gcn_ref.sigmoid(x @ Wt + bt)
+            x = t * h + (1 - t) * x
+        logits = conv(x @ params[k]) + params[k + 1]
+        q.put((rank, r0, r1, first_conv, gcn_ref.softmax_rows(logits)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_feature_sliced_exchange_world3_gloo():
+    """The sliced product must be BIT-identical to the single-process product (every row is summed in CSR order whatever
+    the column slicing); the forward built on it matches the oracle."""
+    import torch.multiprocessing as mp
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_rank_main_sliced, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    A, X, Y, tr, dev, te, cfg = synth.synthetic_problem(dict(n=103, deg=5, f=40, xnnz=6, hid=[44, 44, 44], classes=5))
+    params = gcn_ref.init_params(cfg["f"], cfg["hid"], cfg["classes"], True, 3)
+    x0 = np.tanh(X @ params[0] + params[1])
+    want_first = np.asarray(A @ x0, dtype=np.float32)
+    ref = gcn_ref.forward(params, X, A, cfg["hid"], True)
+    for rank, r0, r1, first_conv, probs in res:
+        np.testing.assert_array_equal(first_conv, want_first[r0:r1])
+        np.testing.assert_allclose(probs, ref["probs"][r0:r1], rtol=1e-4, atol=1e-6)
+
+
+def test_slice_columns_cover_the_operand():
+    for K in (300, 256, 129, 512, 930, 7, 40, 16):
+        for world in (2, 3, 4, 8, 16):
+            col0, width, ldp = partition.slice_columns(K, world)
+            k4 = partition.round_up(K, 4)
+            assert int(width.sum()) == k4 and (width % 4 == 0).all() and (ldp >= width).all() and (ldp % 32 == 0).all()
+            ends = col0 + width
+            assert col0[0] == 0 and (col0[1:][width[1:] > 0] == ends[:-1][width[1:] > 0]).all()
+            assert (col0 % 4 == 0).all() and int(width.max()) - int(width[width > 0].min()) <= 16 + 12
+    assert partition.slice_columns(300, 8)[1].tolist() == [48, 48, 48, 32, 32, 32, 32, 28]
+
+
 def test_hot_column_split_reassembles_x():
     """split_hot_columns: hot CSR (hot-local ids) + cold CSR partition X's nonzeros; hot ids ascending; nothing when the
     matrix has no dense columns."""
@@ -144,3 +244,19 @@ def test_hot_column_split_reassembles_x():
     assert split_hot_columns(X, 0.2, 16)[0] is None          # fewer than 64 hot columns allowed: not worth a GEMM
     # panel working-set rule: 16 MB of 128-byte panel lines per block, at most 8 blocks
     assert panel_col_blocks(62_500) == 1 and panel_col_blocks(500_000) == 4 and panel_col_blocks(10_000_000) == 8
+
+
+def test_hot_columns_are_chosen_globally():
+    """Row blocks given the document frequencies of the WHOLE matrix pick the same hot set as the whole matrix does, so a
+    row's sum is associated the same way on 1 and on P GPUs (bit-equal forward)."""
+    from geographconv_b200.engine import split_hot_columns
+    X = synth.synthetic_features(3000, 400, 40, 3)
+    df = np.bincount(X.indices, minlength=X.shape[1])
+    hot_all, Xh, Xc = split_hot_columns(X.tocsr(), 0.05, 128)
+    assert hot_all is not None
+    for r0, r1 in ((0, 1000), (1000, 3000)):
+        blk = partition.slice_rows(X, r0, r1)
+        hot_b, Xh_b, Xc_b = split_hot_columns(blk, 0.05, 128, df=df, n_total=X.shape[0])
+        np.testing.assert_array_equal(hot_b, hot_all)
+        np.testing.assert_array_equal(Xh_b.toarray(), Xh[r0:r1].toarray())
+        np.testing.assert_array_equal(Xc_b.toarray(), Xc[r0:r1].toarray())
