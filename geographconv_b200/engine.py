@@ -419,15 +419,15 @@ class PeerArena:
 
     def _free_local(self):
         if self.ptr.value:
-            self.self.ctx.call("gcnb_peer_free", self.ptr)
+            self.ctx.call("gcnb_peer_free", self.ptr)
             self.ptr = C.c_void_p()
 
     def close(self):
         """Collective in spirit: every rank unmaps its peers before any rank frees (callers barrier around it)."""
         try:
-            self.self.ctx.call("gcnb_peer_setup", 0, 0, None, 0, 0)
+            self.ctx.call("gcnb_peer_setup", 0, 0, None, 0, 0)
             for pp in self.peers:
-                self.self.ctx.call("gcnb_peer_close", pp)
+                self.ctx.call("gcnb_peer_close", pp)
             self.peers = []
         finally:
             self._free_local()
