@@ -15,7 +15,16 @@ with dropout, cross-entropy metrics, backward, Adam.  Prints ONE JSON line (rank
                B_touch / average launch duration from CUDA events recorded around
                every such launch inside the timed region, against MEASURED_PEAKS.json's HBM copy rate.
 * ``cpu_baseline`` the oracle port (SciPy csr_matvecs single-threaded like Theano's sd_csr + BLAS
-               on all cores) on a bounded sample: a smaller graph with the same per-node statistics.
+               on all cores) on a bounded sample: a smaller graph with the same per-node statistics
+               (the whole graph when the workload is small enough: C1), plus one full-size A_hat.H
+               product and one full-size dense product timed on the host and the op-count
+               extrapolation to the full configuration.
+* ``parity``   in-run proof that THIS run computes the reference's numbers, at every N: a forward
+               pass with the initial weights, 2000 sampled rows of one A_hat.H product and of the
+               final probabilities recomputed in float64 with SciPy from the device's own layer
+               inputs (max relative error, argmax mismatches), and a checksum of the bit patterns
+               of all probabilities that is identical at 1/2/4/8 GPUs iff the row-partitioned
+               forward is bit-identical to the single-GPU one.
 
 ``--impl reference`` times that CPU port alone (rank 0 only); Theano/Lasagne cannot be installed
 here, so ``kind`` is "port".  N > 1: launched by torchrun, one rank per GPU, rows of
@@ -141,6 +150,35 @@ def cpu_step_seconds(problem, steps, warmup):
     return times
 
 
+def cpu_full_size_ops(cfg, A):
+    """One A_hat.H product (SciPy csr_matvecs, one thread = Theano's sd_csr loop) and one N x Hd x Hd dense product
+    (BLAS, all cores) at the workload's FULL size, and the op-count extrapolation of a whole training step from them
+    (SURVEY.md 8d).  Sparse products scale with nnz x columns, dense ones with flops."""
+    n, hd, C = cfg["n"], cfg["hid"][0], cfg["classes"]
+    L = len(cfg["hid"]) - 1
+    rng = np.random.RandomState(1)
+    H = rng.standard_normal((n, hd)).astype(np.float32)
+    W = rng.standard_normal((hd, hd)).astype(np.float32)
+    t0 = time.perf_counter()
+    S = A @ H
+    t_spmm = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    H @ W
+    t_gemm = time.perf_counter() - t0
+    del S
+    per_nnz_col = t_spmm / (A.nnz * hd)
+    per_flop = t_gemm / (2.0 * n * hd * hd)
+    nnz_x = n * cfg["xnnz"]
+    # forward: X.W0, L A-products at Hd, one at C; backward: the same A-products again and X^T.dz
+    sparse = per_nnz_col * (2 * nnz_x * hd + 2 * L * A.nnz * hd + 2 * A.nnz * C)
+    # dense: forward 2 products per highway layer + output; backward twice that
+    dense = per_flop * 3 * (L * 2 * 2.0 * n * hd * hd + 2.0 * n * hd * C)
+    return {"spmm_a_full_s": t_spmm, "gemm_full_s": t_gemm, "extrapolated_step_s": sparse + dense,
+            "extrapolated_nodes_per_s": n / (sparse + dense),
+            "how": "one A_hat.H (N=%d, nnz=%d, K=%d) and one N x %d x %d product timed on the host; step = op counts x those "
+                   "rates (sparse ~ nnz x columns, dense ~ flops)" % (n, A.nnz, hd, hd, hd)}
+
+
 def blas_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -153,7 +191,7 @@ def run_reference(args, cfg, wname):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_s = args.cpu_sample_nodes
+    n_s = min(args.cpu_sample_nodes, cfg["n"])
     prob = cpu_sample_problem(cfg, n_s)
     times = cpu_step_seconds(prob, args.steps, args.warmup)
     sec = float(np.mean(times))
@@ -165,7 +203,7 @@ def run_reference(args, cfg, wname):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_description(wname, cfg), "timing": "host perf_counter",
-                       "sample_nodes": n_s},
+                       "sample_nodes": n_s, "same_config": n_s == cfg["n"]},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                              "host_cpus": len(os.sched_getaffinity(0))},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -221,11 +259,19 @@ def run_gpu(args, cfg, wname):
     def step_resident(i):
         eng.train_step(d_tr, d_dev, len(tr), len(dev), seed=1000 + i)
 
+    hd = cfg["hid"][0]
+    # ---- in-run parity block (initial weights; before anything is trained) ----
+    parity = parity_block(eng, clf, A, cfg, rank, args.parity_rows) if args.parity_rows > 0 else None
+
     # ---- device-resident leg (value) ----
     for i in range(args.warmup):
         step_resident(i)
     eng.read_metrics()
     barrier()
+    # inside the timed region only the dominant kernel (the A_hat.H product at the hidden width) carries CUDA events;
+    # the full per-op split comes from an instrumented pass of the same steps afterwards (two event records around every
+    # one of the ~80 ops of a step are measurable at 7 ms per step)
+    eng.ctx.set_option("prof_mask", 1 << capi_tag("spmm_a"))
     eng.ctx.prof_enable(True)
     eng.ctx.prof_reset()
     launches0 = eng.ctx.launch_count()
@@ -234,16 +280,17 @@ def run_gpu(args, cfg, wname):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_host0 = time.perf_counter()
     e0.record(eng.stream)  # the stream every kernel of the step is launched on
     for i in range(args.steps):
         step_resident(args.warmup + i)
     e1.record(eng.stream)
+    t_issue = time.perf_counter() - t_host0  # host time to enqueue the steps (must stay below the device time)
     barrier()
     clocks = sampler.stop() if sampler else None
     ms = e0.elapsed_time(e1)
     launches = eng.ctx.launch_count() - launches0
     prof = eng.ctx.prof_collect()
-    eng.ctx.prof_enable(False)
     metrics = eng.read_metrics()
     tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -253,36 +300,64 @@ def run_gpu(args, cfg, wname):
     value = N / (ms_per_step * 1e-3)
 
     # roofline of the dominant kernel: A_hat.H SpMM at the hidden width (tag spmm_a)
-    hd = cfg["hid"][0]
     spmm_ms, spmm_ops = prof["spmm_a"]
     peak, peak_kind = load_peaks()
     b_touch = eng.conv_touched_bytes(hd)
-    pieces = len(eng._panels(hd, eng.ldh[0], False)) if world > 1 else 1  # SpMM launches per graph convolution
+    w_mine = int(eng._slice_plan(hd)[1][eng.rank]) if eng.exchange == "slice" else hd
+    n_rows_prod = eng.A.shape[0]
+    b_min = eng.A.nnz * 8 + (n_rows_prod + 1) * 4 + (eng.A.shape[1] + n_rows_prod) * w_mine * 4
+    pieces = len(eng._panels(hd, eng.ldh[0], False)) if eng.exchange == "gather" else 1  # SpMM launches per convolution
     roof = None
-    traffic = args.ncu_traffic_bytes
+    kname = "spmm_panel_kernel" if eng.exchange == "slice" else \
+        ["spmm_ldg_kernel", "spmm_bulk_kernel", "spmm_panel_kernel"][eng.A.engine_for(eng, eng.ldh[0], hd)]
+    traffic, l2_hit, traffic_src = args.ncu_traffic_bytes, None, "--ncu-traffic-bytes" if args.ncu_traffic_bytes else None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    kname = ["spmm_ldg_kernel", "spmm_bulk_kernel", "spmm_panel_kernel"][eng.A.engine_for(eng, eng.ldh[0], hd)]
     if traffic is None and world == 1 and os.path.exists(tpath):
         tj = json.load(open(tpath))
-        if tj.get("workload") == wname and args.alpha is None and tj.get("kernel", "").startswith(kname):
-            traffic = tj["dram_bytes_per_launch"]  # from the committed ncu --set full capture of this kernel
+        if tj.get("workload") == wname and args.alpha is None and kname in tj.get("kernel", ""):
+            traffic, l2_hit = tj["dram_bytes_per_launch"], tj.get("l2_hit_pct")  # committed ncu --set full capture
+            traffic_src = tj.get("source")
     if spmm_ops:
         t_launch = spmm_ms / (spmm_ops / pieces) * 1e-3  # all pieces of one product
         ach = b_touch / t_launch / 1e9
         tms2 = torch.tensor([ach], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tms2, op=dist.ReduceOp.MIN)  # slowest rank's kernel
+        scale = float(tms2.item()) / ach
         ach = float(tms2.item())
+        t_launch = t_launch / scale
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic,
-                "kernel": "%s (A_hat.H, K=%d)" % (kname, hd),
-                "algorithmic_bytes_per_launch": b_touch, "launches_timed": spmm_ops, "launches_per_product": pieces,
-                "avg_launch_ms": spmm_ms / spmm_ops * pieces, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
-                "per_rank": world > 1}
+                "kernel": "%s (A_hat.H, K=%d%s)" % (kname, hd, ", column slice of %d" % w_mine if eng.exchange == "slice" else ""),
+                "algorithmic_bytes_per_launch": b_touch, "compulsory_bytes_per_launch": b_min,
+                "launches_timed": spmm_ops, "launches_per_product": pieces,
+                "avg_launch_ms": t_launch * 1e3, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
+                "per_rank": world > 1,
+                # the physical side of the same launch: DRAM bytes ncu counted / the live launch time
+                "frac_dram": (traffic / t_launch / 1e9 / peak) if traffic else None,
+                "frac_compulsory": b_min / t_launch / 1e9 / peak,
+                "l2_hit_pct": l2_hit, "traffic_source": traffic_src}
         if kname == "spmm_panel_kernel":
-            roof["note"] = ("L2-resident column panels: B leaves HBM once per product, the per-nonzero gathers are L2 hits, so "
-                            "algorithmic B_touch / t may exceed the HBM peak; `traffic` is the DRAM bytes ncu counted")
-    split = {k: round(v[0] / args.steps, 4) for k, v in prof.items()}
+            roof["note"] = ("L2-resident column panels: B leaves HBM once per product and the per-nonzero gathers are L2 hits, so "
+                            "`frac` (algorithmic B_touch / t over the HBM peak, the contract's definition) may exceed 1; "
+                            "`frac_dram` is ncu's DRAM bytes over the same time, `frac_compulsory` the perfect-reuse bytes")
+
+    # ---- instrumented pass: per-op split (every tag timed), NCCL collectives timed with their own events ----
+    split_steps = max(1, min(args.steps, 5))
+    eng.ctx.set_option("prof_mask", -1)
+    eng.ctx.prof_reset()
+    eng.time_nccl = True
+    eng.nccl_ms()
+    barrier()
+    for i in range(split_steps):
+        step_resident(args.warmup + args.steps + i)
+    barrier()
+    prof_all = eng.ctx.prof_collect()
+    eng.ctx.prof_enable(False)
+    split = {k: round(v[0] / split_steps, 4) for k, v in prof_all.items()}
+    split["nccl"] = round(eng.nccl_ms() / split_steps, 4)
+    eng.time_nccl = False
+    split["comm_total"] = round(split.get("comm", 0.0) + split.get("sync", 0.0) + split["nccl"], 4)
 
     # ---- end-to-end leg through GraphConv.f_train with host buffers ----
     e2e_steps = max(0, min(args.steps, args.e2e_steps))
@@ -308,6 +383,10 @@ def run_gpu(args, cfg, wname):
                "d2h_bytes_per_step": 32 * world, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                "api": "GraphConv.f_train(X, y_train, y_dev, A, train_idx, dev_idx), host SciPy/NumPy inputs"}
     clf.cache_device_inputs = True
+    mem_peak = torch.tensor([float(torch.cuda.max_memory_allocated() + (eng.arena.nbytes if eng.arena is not None else 0))],
+                            dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(mem_peak, op=dist.ReduceOp.MAX)
 
     line = None
     if rank == 0:
@@ -315,30 +394,102 @@ def run_gpu(args, cfg, wname):
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload_description(wname, cfg), "parallelism": "rows/%d" % world,
-                           "l2": "inputs larger than L2 (each N x Hd activation is %.0f MB)" % (N / world * 320 * 4 / 1e6),
+                           "exchange": {"slice": "feature-sliced A_hat.H over NVLink peer memory (A_hat replicated)",
+                                        "gather": "NCCL all-gather of the dense operand", "none": "single GPU"}[eng.exchange],
+                           "l2": "inputs larger than L2 (each N x Hd activation is %.0f MB)" % (N / world * eng.ldh[0] * 4 / 1e6),
                            "spmm_variant": eng.ctx.get_option("spmm_variant"), "gemm_tc": eng.ctx.get_option("gemm_tc"),
                            "power_law_alpha": args.alpha, "nnz_A": int(A.nnz), "nnz_X": int(X.nnz)},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": e2e,
                 "roofline": roof, "split_ms_per_step": split,
+                "split_note": "per-op CUDA events from an instrumented pass of %d further steps (rank 0); `sync` = peer "
+                              "barriers incl. waiting for the slowest rank, `comm` = slice pushes not fused into a producer, "
+                              "`nccl` = all-gather / all-reduce collectives" % split_steps,
+                "host_issue_ms_per_step": t_issue / args.steps * 1e3,
+                "peak_device_bytes_per_rank": int(mem_peak.item()),
+                "exchange_bytes_per_product": eng.conv_exchange_bytes(hd),
+                "parity": parity,
                 "last_metrics": {"train_loss": metrics[0], "train_acc": metrics[1], "dev_loss": metrics[2],
                                  "dev_acc": metrics[3]},
                 "setup_s": {"generate": round(t_gen, 1), "prepare_and_upload": round(t_bind, 1)}}
         if not args.no_cpu_baseline and world == 1:
-            n_s = args.cpu_sample_nodes
+            n_s = min(args.cpu_sample_nodes, cfg["n"])
             times = cpu_step_seconds(cpu_sample_problem(cfg, n_s), 1, 1)
             cores = blas_threads()
             line["cpu_baseline"] = {
                 "value": n_s / float(np.mean(times)), "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": "oracle port (SciPy csr_matvecs 1 thread like Theano sd_csr; OpenBLAS %d threads) on a "
-                          "%d-node graph with the workload's per-node statistics, 1 warm + 1 timed step" % (cores, n_s),
+                "sample": "oracle port (SciPy csr_matvecs 1 thread like Theano sd_csr; OpenBLAS %d threads) on %s, 1 warm + 1 "
+                          "timed step" % (cores, "the whole workload" if n_s == cfg["n"] else
+                                          "a %d-node graph with the workload's per-node statistics" % n_s),
+                "same_config": n_s == cfg["n"],
                 "host_cpus": len(os.sched_getaffinity(0))}
+            if n_s != cfg["n"] and not args.no_cpu_full_ops:
+                line["cpu_baseline"]["full_size_ops"] = cpu_full_size_ops(cfg, A)
         else:
             line["cpu_baseline"] = None
         emit(line)
     if world > 1:
         dist.barrier()
+    clf.close()
+    if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def capi_tag(name):
+    from geographconv_b200 import capi
+    return capi.TAGS.index(name)
+
+
+def parity_block(eng, clf, A, cfg, rank, n_rows):
+    """In-run parity (every N; collective): one forward pass with the initial weights and a fixed dropout seed, then
+    * ``forward_checksum``: checksum of the bit patterns of all N x C probabilities (identical at every GPU count iff the
+      row-partitioned forward is bit-identical to the single-GPU forward);
+    * ``spmm``: ``n_rows`` sampled rows of S = A_hat.H0 recomputed in float64 with SciPy from the device's own H0 rows;
+    * ``probs``: the same rows of P = softmax(A_hat.(Y.Wout) + bout) recomputed in float64 from the device's own last
+      hidden layer Y; argmax compared on every sampled row.
+    Errors are relative to the largest reference magnitude (products) / element-wise relative (probabilities)."""
+    import scipy.sparse as sp
+    n, hd, C = cfg["n"], cfg["hid"][0], cfg["classes"]
+    seed = 424242
+    eng.forward(train=True, seed=seed)
+    checksum = eng.checksum(eng.P, eng.n_loc, C)
+    rng = np.random.RandomState(12345)
+    rows = np.sort(rng.choice(n, size=min(n_rows, n), replace=False))
+    sub = A[rows].tocsr()
+    nb = np.unique(sub.indices)
+    remap = np.full(n, -1, dtype=np.int64)
+    remap[nb] = np.arange(len(nb))
+    sub64 = sp.csr_matrix((sub.data.astype(np.float64), remap[sub.indices], sub.indptr), shape=(len(rows), len(nb)))
+    # (1) one A_hat.H product through the engine's exchange path: S = A_hat.H0
+    S = eng.S.view(-1)[: eng.nbuf * eng.ldh[0]].view(eng.nbuf, eng.ldh[0])
+    eng._conv(eng.H0, eng.A, S, eng.ldh[0], hd)
+    s_gpu = eng.read_rows(S, rows, hd)
+    h0_nb = eng.read_rows(eng.H0, nb, hd)
+    # (2) final probabilities from the device's own last hidden layer
+    p_gpu = eng.read_rows(eng.P, rows, C)
+    y_nb = eng.read_rows(eng.x_last, nb, eng.w_last)
+    out = None
+    if rank == 0:
+        s_ref = sub64 @ h0_nb.astype(np.float64)
+        spmm_err = float(np.abs(s_gpu - s_ref).max() / max(np.abs(s_ref).max(), 1e-30))
+        params = clf.init_params
+        Wout, bout = params[-2].astype(np.float64), params[-1].astype(np.float64)
+        logits = sub64 @ (y_nb.astype(np.float64) @ Wout) + bout[None, :]
+        logits -= logits.max(axis=1, keepdims=True)
+        p_ref = np.exp(logits)
+        p_ref /= p_ref.sum(axis=1, keepdims=True)
+        probs_err = float((np.abs(p_gpu - p_ref) / p_ref).max())
+        mism = np.nonzero(p_gpu.argmax(1) != p_ref.argmax(1))[0]
+        top2 = np.sort(p_ref[mism], axis=1)[:, -2:] if len(mism) else np.zeros((0, 2))
+        out = {"rows_sampled": int(len(rows)), "forward_checksum": "%012x" % checksum,
+               "spmm_max_rel": spmm_err, "probs_max_rel": probs_err, "max_rel": max(spmm_err, probs_err),
+               "argmax_mismatch": int(len(mism)),
+               "argmax_mismatch_top2_rel_gap": [float((b - a) / b) for a, b in top2],
+               "tolerance": 1e-3,
+               "how": "float64 SciPy on rank 0 from the device's own layer inputs; seed %d, initial weights" % seed}
+        assert out["max_rel"] <= 1e-3, "in-run parity failed: %r" % out
+    return out
 
 
 _JSON_FD = None
@@ -368,6 +519,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample-nodes", type=int, default=32768)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-full-ops", action="store_true", help="skip the full-size host SpMM / GEMM timing")
+    ap.add_argument("--parity-rows", type=int, default=2000, help="rows of the in-run parity block (0 = skip)")
     ap.add_argument("--ncu-traffic-bytes", type=float, default=None,
                     help="dram bytes per launch of the dominant kernel from the committed ncu capture")
     args = ap.parse_args()

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libgcnb200.so")
 
 OK, E_INVALID, E_CUDA, E_WORKSPACE, E_UNSUPPORTED = 0, -1, -2, -3, -4
 ACT = {"linear": 0, "tanh": 1, "relu": 2, "rectify": 2, "sigmoid": 3, "selu": 4, None: 0}
-TAGS = ["spmm_a", "spmm_x", "spmm_xt", "gemm", "elementwise", "loss", "adam", "copy", "spmm_a_narrow", "comm"]
+TAGS = ["spmm_a", "spmm_x", "spmm_xt", "gemm", "elementwise", "loss", "adam", "copy", "spmm_a_narrow", "comm", "sync"]
 TAG_SPMM_A, TAG_SPMM_X, TAG_SPMM_XT, TAG_SPMM_A_NARROW = 0, 1, 2, 8
 
 
@@ -85,6 +85,9 @@ SIGNATURES = {
     "gcnb_scatter_rows_f32": (C.c_int, [_ctxp, _vp, _i32, _vp, _i32, _i32, _vp, _i32]),
     "gcnb_xent_metrics_f32": (C.c_int, [_ctxp, _vp, _i32, _i32, _vp, _vp, _i32, _vp]),
     "gcnb_xent_grad_f32": (C.c_int, [_ctxp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _f32, _vp, _i32]),
+    "gcnb_xent_grad_dense_f32": (C.c_int, [_ctxp, _vp, _i32, _i32, _i32, _vp, _f32, _vp, _i32]),
+    "gcnb_push_arm": (C.c_int, [_ctxp, _vp, _i32, _vp, _vp, _vp, _i64]),
+    "gcnb_push_consumed": (C.c_int, [_ctxp]),
     "gcnb_gather_argmax_f32": (C.c_int, [_ctxp, _vp, _i32, _i32, _vp, _i32, _vp, _vp]),
     "gcnb_geo_distance_f64": (C.c_int, [_ctxp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, C.c_double, _vp, _vp]),
     "gcnb_l1l2_f32": (C.c_int, [_ctxp, _vp, _vp, _i64, _f32, _vp]),

@@ -103,6 +103,7 @@ static int* option_slot(gcnb_ctx* ctx, const char* name) {
   if (!strcmp(name, "spmm_panel")) return &ctx->spmm_panel;
   if (!strcmp(name, "spmm_panel_policy")) return &ctx->spmm_panel_policy;
   if (!strcmp(name, "peer_timeout_s")) return &ctx->peer_timeout_s;
+  if (!strcmp(name, "prof_mask")) return reinterpret_cast<int*>(&ctx->prof_mask);
   if (!strcmp(name, "tc_dbg_mode")) return &ctx->tc_dbg_mode;
   if (!strcmp(name, "tc_launches")) return &ctx->tc_launches;
   return nullptr;

@@ -15,6 +15,21 @@ struct ProfPair {
   int tag;
 };
 
+// Fused "rows -> column slices" transpose of the feature-sliced exchange (peer.cu): a producer kernel that is armed with
+// a PushPlan stores its output row block straight into the owners' panel buffers over NVLink, instead of (or besides)
+// writing it locally for gcnb_slice_push_f32 to copy.  Passed by value as a kernel parameter.
+constexpr int kPushUnit = 16;       // slices are runs of 16-column units (partition.slice_columns)
+constexpr int kPushMaxUnits = 64;   // operands up to 1024 columns
+struct PushPlan {
+  float* xp[GCNB_MAX_PEERS];   // rank q's panel buffer
+  int col0[GCNB_MAX_PEERS];    // first column of q's slice
+  int ldp[GCNB_MAX_PEERS];     // leading dimension of q's panel buffer
+  unsigned char owner[kPushMaxUnits];  // owner of every 16-column unit
+  long long row0;              // global index of local row 0
+  int k4;                      // operand width rounded up to 4
+  int on;
+};
+
 struct gcnb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -41,8 +56,12 @@ struct gcnb_ctx {
   size_t peer_bytes = 0;
   size_t peer_flags_offset = 0;
   int peer_timeout_s = 30;
+  PushPlan push_plan;          // armed by gcnb_push_arm, taken by the next producer that supports it
+  bool push_armed = false;
+  bool push_consumed = false;
   // profiling
   bool prof = false;
+  unsigned prof_mask = 0xffffffffu;  // tags that are timed while profiling is on
   std::vector<ProfPair> pending;
   std::vector<cudaEvent_t> pool;
   float prof_ms[GCNB_NTAGS] = {0};
@@ -97,7 +116,7 @@ struct ProfScope {
     return e;
   }
   ProfScope(gcnb_ctx* c, int t) : ctx(c), tag(t) {
-    if (ctx->prof) {
+    if (ctx->prof && ((ctx->prof_mask >> t) & 1u)) {
       a = get(ctx);
       b = get(ctx);
       cudaEventRecord(a, ctx->stream);
@@ -113,6 +132,19 @@ struct ProfScope {
 
 // local arena pointer -> the same offset in rank q's arena; nullptr when [p, p + span) is not inside the local arena
 void* gcnb_peer_translate(const gcnb_ctx* ctx, const void* p, int q, size_t span);
+
+// the armed push plan if it matches an output of `k` columns (and disarm), else a plan with on == 0
+static inline PushPlan gcnb_take_push(gcnb_ctx* ctx, int k) {
+  PushPlan pp;
+  memset(&pp, 0, sizeof(pp));
+  if (ctx->push_armed && ctx->push_plan.k4 == ((k + 3) / 4) * 4) {
+    pp = ctx->push_plan;
+    pp.on = 1;
+    ctx->push_armed = false;
+    ctx->push_consumed = true;
+  }
+  return pp;
+}
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
@@ -191,6 +223,14 @@ __device__ __forceinline__ float4 ld_gather_f4(const float4* p) {
 __device__ __forceinline__ void st_stream_f4(float4* p, float4 v) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
+}
+
+// store one float4 (columns c .. c+3 of local row r) into the panel buffer of the rank that owns those columns
+__device__ __forceinline__ void push_store_f4(const PushPlan& pp, long long r, int c, float4 v) {
+  if (c >= pp.k4) return;
+  const int q = pp.owner[c >> 4];
+  float4* dst = reinterpret_cast<float4*>(pp.xp[q] + (size_t)(pp.row0 + r) * pp.ldp[q] + (c - pp.col0[q]));
+  *dst = v;
 }
 
 __device__ __forceinline__ float warp_max(float v) {

@@ -149,7 +149,7 @@ template <int NCH>
 __global__ void __launch_bounds__(kThreads) highway_bwd_colsum_kernel(int n_rows, int nf4, int ld, const float* dY,
                                                                       const float* X, const float* H, const float* T,
                                                                       int act, float* dH, float* dT, float* dX,
-                                                                      float* partial) {
+                                                                      float* partial, const PushPlan pp) {
   __shared__ float4 red[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4 sH[NCH], sT[NCH];
@@ -171,7 +171,10 @@ __global__ void __launch_bounds__(kThreads) highway_bwd_colsum_kernel(int n_rows
   sT[ch].e += dt.e;
         GCNB_HW_BWD(x) GCNB_HW_BWD(y) GCNB_HW_BWD(z) GCNB_HW_BWD(w)
 #undef GCNB_HW_BWD
-        st4(dH, (size_t)r, ld, c, dh);
+        // dHpre only feeds the graph convolution V = A^T.dHpre: in a feature-sliced run it goes straight to the
+        // ranks that own its columns (NVLink stores riding under this kernel's HBM traffic), not to local memory
+        if (pp.on) push_store_f4(pp, r, 4 * c, dh);
+        else st4(dH, (size_t)r, ld, c, dh);
         st4(dT, (size_t)r, ld, c, dt);
         st4(dX, (size_t)r, ld, c, dx);
       }
@@ -190,7 +193,8 @@ __global__ void __launch_bounds__(kThreads) highway_bwd_colsum_kernel(int n_rows
 template <int NCH>
 __global__ void __launch_bounds__(kThreads) act_bwd_colsum_kernel(int n_rows, int nf4, int ld, const float* dY,
                                                                   const float* Yact, int act, uint32_t thresh, float scale,
-                                                                  uint64_t seed, int64_t row0, float* dZ, float* partial) {
+                                                                  uint64_t seed, int64_t row0, float* dZ, float* partial,
+                                                                  const PushPlan pp) {
   __shared__ float4 red[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4 sZ[NCH];
@@ -217,7 +221,8 @@ __global__ void __launch_bounds__(kThreads) act_bwd_colsum_kernel(int n_rows, in
           o.w = g.w * act_grad_from_out(act, y.w);
         }
         sZ[ch].x += o.x; sZ[ch].y += o.y; sZ[ch].z += o.z; sZ[ch].w += o.w;
-        st4(dZ, (size_t)r, ld, c, o);
+        if (pp.on) push_store_f4(pp, r, 4 * c, o);  // operand of the next graph convolution: to its column owners
+        else st4(dZ, (size_t)r, ld, c, o);
       }
     }
   }
@@ -283,6 +288,32 @@ __global__ void __launch_bounds__(kThreads) xent_grad_kernel(const float* P, int
   const float* row = P + (size_t)r * ldp;
   float* g = G + (size_t)r * ldg;
   for (int c = lane; c < C; c += 32) atomicAdd(g + c, (row[c] - (c == y ? 1.f : 0.f)) * inv_n);
+}
+
+// dense form of the loss gradient: row_label[r] = class of local row r if it is a training row, else -1.  A warp per
+// row writes the whole row of G (zeros for non-training rows), locally for the bias gradient and -- armed -- into the
+// panel buffers of the column owners for the graph convolution A^T.G that follows.
+__global__ void __launch_bounds__(kThreads) xent_grad_dense_kernel(const float* P, int ldp, int C, int n_rows,
+                                                                   const int* row_label, float inv_n, float* G, int ldg,
+                                                                   const PushPlan pp) {
+  const int lane = threadIdx.x & 31;
+  const int nf4 = (C + 3) >> 2;
+  for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < n_rows; r += (long long)gridDim.x * 8) {
+    const int y = row_label[r];
+    for (int c4 = lane; c4 < nf4; c4 += 32) {
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (y >= 0) {
+        const float4 pr = ld4(P, (size_t)r, ldp, c4);
+        const int c = 4 * c4;
+        g.x = c + 0 < C ? (pr.x - (c + 0 == y ? 1.f : 0.f)) * inv_n : 0.f;
+        g.y = c + 1 < C ? (pr.y - (c + 1 == y ? 1.f : 0.f)) * inv_n : 0.f;
+        g.z = c + 2 < C ? (pr.z - (c + 2 == y ? 1.f : 0.f)) * inv_n : 0.f;
+        g.w = c + 3 < C ? (pr.w - (c + 3 == y ? 1.f : 0.f)) * inv_n : 0.f;
+      }
+      st4(G, (size_t)r, ldg, c4, g);
+      if (pp.on) push_store_f4(pp, r, 4 * c4, g);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kThreads) gather_argmax_kernel(const float* P, int ldp, int C, const int* idx,
@@ -450,9 +481,10 @@ extern "C" int gcnb_highway_bwd_bias_f32(gcnb_ctx* ctx, int32_t n_rows, int32_t 
   if (blocks > kMaxReduceBlocks) blocks = kMaxReduceBlocks;
   float* partial = reinterpret_cast<float*>(ctx->ws);
   const int nch = (nf4 + 31) / 32;
+  const PushPlan pp = gcnb_take_push(ctx, hd);
 #define GCNB_LAUNCH_HWB(N)                                                                                         \
   highway_bwd_colsum_kernel<N><<<blocks, kThreads, 0, ctx->stream>>>(n_rows, nf4, ld, dY, X, H, T, act, dHpre, dTpre, \
-                                                                     dX, partial)
+                                                                     dX, partial, pp)
   if (nch <= 1) GCNB_LAUNCH_HWB(1);
   else if (nch == 2) GCNB_LAUNCH_HWB(2);
   else if (nch == 3) GCNB_LAUNCH_HWB(3);
@@ -489,9 +521,10 @@ extern "C" int gcnb_act_bwd_bias_f32(gcnb_ctx* ctx, int32_t n_rows, int32_t k, i
   float* partial = reinterpret_cast<float*>(ctx->ws);
   const float scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
   const int nch = (nf4 + 31) / 32;
+  const PushPlan pp = gcnb_take_push(ctx, k);
 #define GCNB_LAUNCH_AB(N)                                                                                      \
   act_bwd_colsum_kernel<N><<<blocks, kThreads, 0, ctx->stream>>>(n_rows, nf4, ld, dY, Yact, act, thresh_of(dropout_p), \
-                                                                 scale, seed, row0, dZ, partial)
+                                                                 scale, seed, row0, dZ, partial, pp)
   if (nch <= 1) GCNB_LAUNCH_AB(1);
   else if (nch == 2) GCNB_LAUNCH_AB(2);
   else if (nch == 3) GCNB_LAUNCH_AB(3);
@@ -575,6 +608,24 @@ extern "C" int gcnb_xent_grad_f32(gcnb_ctx* ctx, const float* P, int32_t ldp, in
   GCNB_CUDA(ctx, cudaMemsetAsync(G, 0, (size_t)n_rows * ldg * sizeof(float), ctx->stream));
   if (n_idx == 0) return GCNB_OK;
   xent_grad_kernel<<<cdiv(n_idx, 8), kThreads, 0, ctx->stream>>>(P, ldp, n_classes, idx, labels, n_idx, inv_n, G, ldg);
+  GCNB_LAUNCHED(ctx);
+  return GCNB_OK;
+}
+
+extern "C" int gcnb_xent_grad_dense_f32(gcnb_ctx* ctx, const float* P, int32_t ldp, int32_t n_classes, int32_t n_rows,
+                                        const int32_t* row_label, float inv_n, float* G, int32_t ldg) {
+  if (!ctx) return GCNB_E_INVALID;
+  GCNB_REQUIRE(ctx, P && G && (n_rows == 0 || row_label), "null pointer");
+  const int c4 = ((n_classes + 3) / 4) * 4;
+  GCNB_REQUIRE(ctx, ldp % 4 == 0 && ldg % 4 == 0 && ldp >= c4 && ldg >= c4 && aligned16(P) && aligned16(G),
+               "ldp / ldg: multiple of 4, >= classes rounded to 4; 16-byte aligned");
+  if (n_rows == 0) return GCNB_OK;
+  ProfScope scope(ctx, GCNB_TAG_LOSS);
+  const PushPlan pp = gcnb_take_push(ctx, n_classes);
+  int blocks = cdiv(n_rows, 8);
+  const int cap = ctx->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  xent_grad_dense_kernel<<<blocks, kThreads, 0, ctx->stream>>>(P, ldp, n_classes, n_rows, row_label, inv_n, G, ldg, pp);
   GCNB_LAUNCHED(ctx);
   return GCNB_OK;
 }

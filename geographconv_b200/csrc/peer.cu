@@ -181,7 +181,7 @@ void* gcnb_peer_translate(const gcnb_ctx* ctx, const void* p, int q, size_t span
 extern "C" int gcnb_peer_barrier(gcnb_ctx* ctx) {
   if (!ctx) return GCNB_E_INVALID;
   GCNB_REQUIRE(ctx, ctx->peer_world >= 2, "no peer arena attached (gcnb_peer_setup)");
-  ProfScope scope(ctx, GCNB_TAG_COMM);
+  ProfScope scope(ctx, GCNB_TAG_SYNC);
   PeerTab tab;
   memset(&tab, 0, sizeof(tab));
   for (int q = 0; q < ctx->peer_world; ++q)
@@ -221,4 +221,46 @@ extern "C" int gcnb_slice_push_f32(gcnb_ctx* ctx, const float* x, int32_t ldx, i
   slice_push_kernel<<<grid, 256, 0, ctx->stream>>>(p);
   GCNB_LAUNCHED(ctx);
   return GCNB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ fused push
+extern "C" int gcnb_push_arm(gcnb_ctx* ctx, float* xp_local, int32_t K, const int32_t* col0, const int32_t* width,
+                             const int32_t* ldp, int64_t row0) {
+  if (!ctx) return GCNB_E_INVALID;
+  ctx->push_armed = false;
+  ctx->push_consumed = false;
+  GCNB_REQUIRE(ctx, ctx->peer_world >= 2, "no peer arena attached (gcnb_peer_setup)");
+  GCNB_REQUIRE(ctx, xp_local && col0 && width && ldp && K > 0, "null pointer");
+  const int k4 = ((K + 3) / 4) * 4;
+  if ((k4 + kPushUnit - 1) / kPushUnit > kPushMaxUnits) return GCNB_E_UNSUPPORTED;
+  PushPlan pp;
+  memset(&pp, 0, sizeof(pp));
+  pp.row0 = row0;
+  pp.k4 = k4;
+  int next = 0;
+  for (int q = 0; q < ctx->peer_world; ++q) {
+    GCNB_REQUIRE(ctx, col0[q] % 4 == 0 && width[q] % 4 == 0 && ldp[q] % 4 == 0 && width[q] >= 0 && ldp[q] >= width[q],
+                 "slice: columns in multiples of 4");
+    pp.xp[q] = reinterpret_cast<float*>(gcnb_peer_translate(ctx, xp_local, q, 16));
+    GCNB_REQUIRE(ctx, pp.xp[q] != nullptr, "panel buffer is not inside the peer arena");
+    pp.col0[q] = col0[q];
+    pp.ldp[q] = ldp[q];
+    if (width[q] == 0) continue;
+    // slices are contiguous runs of whole 16-column units in rank order (the last one may be cut at k4)
+    GCNB_REQUIRE(ctx, col0[q] == next && col0[q] % kPushUnit == 0, "slices must tile the columns in rank order, unit-aligned");
+    for (int c = col0[q]; c < col0[q] + width[q]; c += kPushUnit) pp.owner[c / kPushUnit] = (unsigned char)q;
+    next = col0[q] + ((width[q] + kPushUnit - 1) / kPushUnit) * kPushUnit;
+  }
+  GCNB_REQUIRE(ctx, next >= k4, "slices do not cover the operand");
+  ctx->push_plan = pp;
+  ctx->push_armed = true;
+  return GCNB_OK;
+}
+
+extern "C" int gcnb_push_consumed(gcnb_ctx* ctx) {
+  if (!ctx) return 0;
+  const int done = ctx->push_consumed ? 1 : 0;
+  ctx->push_armed = false;
+  ctx->push_consumed = false;
+  return done;
 }

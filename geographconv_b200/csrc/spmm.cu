@@ -65,6 +65,9 @@ struct SpmmParams {
   int out_col0;
   int n_pad;       // 0: every row is stored through C
   float* peer_C[GCNB_MAX_PEERS];
+  // fused push (gcnb_push_arm): the finished output row block also goes to the owners of its columns, as the operand
+  // of the feature-sliced graph convolution that follows (first layer: H0 = dropout(act(X.W0 + b0)))
+  PushPlan push;
 };
 
 // first element of output row `row`: local C, or the owning rank's copy of C in a feature-sliced product
@@ -184,6 +187,7 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, floa
         o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
       }
       st_stream_f4(crow + f4, o);
+      if (p.push.on) push_store_f4(p.push, row, gcol0 + 4 * f4, o);
     }
   }
 }
@@ -441,6 +445,7 @@ __device__ __forceinline__ void panel_epilogue(const SpmmParams& p, int row, int
     o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
   }
   st_stream_f4(cptr, o);
+  if (p.push.on) push_store_f4(p.push, row, c, o);
 }
 
 // GL lanes per row item (panel = 4*GL floats), R (column, value) pairs per lane and batch: GL*R gathers in flight.
@@ -882,6 +887,7 @@ extern "C" int gcnb_spmm_csr_f32(gcnb_ctx* ctx, const gcnb_csr* A, const float* 
     }
     p.seed = epi->seed; p.row0 = epi->row0; p.logits = epi->logits;
   }
+  if (!p.softmax) p.push = gcnb_take_push(ctx, K);  // a softmax output is never a convolution operand
   // a row softmax over more than one register pass of columns runs as a pass of its own after the product + bias
   const bool wide_softmax = p.softmax && K > kMaxPassCols;
   float* const wide_logits = p.logits;

@@ -521,6 +521,8 @@ class Engine:
         self.ws = None
         self._measuring = False
         self._measured = 0
+        self.time_nccl = False
+        self._nccl_events = []
         self._keepalive = []
         self.n = None  # rows bound (global)
         self.A = self.X = self.XT = self.AT = None
@@ -528,6 +530,7 @@ class Engine:
         self._bound_refs = None
         self.host = None
         self._idx_cache = {}
+        self._row_labels = {}
         self.h2d_bytes_last_bind = 0
         self.step_count = 0
 
@@ -665,6 +668,7 @@ class Engine:
             self._alloc_buffers(need_backward)
             self._bound_key = key
             self._idx_cache = {}
+            self._row_labels = {}
         else:
             hg = self.host
             # same host objects, fresh copies: on the copy stream, in order of first use, one event per group
@@ -821,10 +825,17 @@ class Engine:
         li, ll = _pinned(li), _pinned(ll)
         d_idx = self.upload(li)
         d_lab = self.upload(ll) if have_labels else None
+        if have_labels and len(np.unique(li)) == len(li):
+            # dense label map for the one-pass loss gradient (gcnb_xent_grad_dense_f32); an index set that names a row
+            # twice counts it twice in the reference's mean (gcnmodel.py:376,382) and keeps the scatter-add kernel
+            rl = np.full(max(self.nbuf, 1), -1, dtype=np.int32)
+            rl[li] = ll
+            self._row_labels[d_idx.data_ptr()] = self.upload(rl)
         self.ctx.sync()
         self._keepalive = []
         if len(self._idx_cache) >= 16:
-            self._idx_cache.pop(next(iter(self._idx_cache)))
+            old = self._idx_cache.pop(next(iter(self._idx_cache)))
+            self._row_labels.pop(old[0].data_ptr(), None)
         self._idx_cache[key] = (d_idx, d_lab, len(li), idx.copy(), li, ll, labels.copy() if have_labels else None)
         return d_idx, d_lab, len(li)
 
@@ -854,16 +865,58 @@ class Engine:
             return [(0, ld, K)]
         return [(c0, min(w, ld - c0), min(K - c0, min(w, ld - c0))) for c0 in range(0, ld, w) if c0 < K]
 
-    def _conv_begin(self, x, K, whole=False):
+    # CUDA-event timing of the NCCL collectives (bench.py's split; off by default)
+    def _nccl_tick(self, stream):
+        if not self.time_nccl:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(stream)
+        return e
+
+    def _nccl_tock(self, t0, stream):
+        if t0 is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)
+            self._nccl_events.append((t0, e))
+
+    def nccl_ms(self, reset=True):
+        """Milliseconds spent inside NCCL collectives since the last reset (device time; blocks)."""
+        self.ctx.sync()
+        if self.comm is not None:
+            self.comm.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in self._nccl_events)
+        if reset:
+            self._nccl_events = []
+        return ms
+
+    def _arm_push(self, K):
+        """Feature-sliced runs: let the NEXT producer kernel store its K-column output straight into the owners' panel
+        buffers (gcnb_push_arm).  Returns True when armed; pair with ``_push_done``."""
+        if self.exchange != "slice":
+            return False
+        col0, width, ldp = self._slice_plan(K)
+        rc = self.lib.gcnb_push_arm(self.ctx.h, _ptr(self.XP), int(K), C.c_void_p(col0.ctypes.data),
+                                    C.c_void_p(width.ctypes.data), C.c_void_p(ldp.ctypes.data), int(self.r0))
+        if rc == capi.E_UNSUPPORTED:
+            return False
+        self.ctx.check(rc)
+        return True
+
+    def _push_done(self, armed):
+        """True when the producer that ran since ``_arm_push`` pushed its output (no explicit push needed)."""
+        return bool(armed) and bool(self.lib.gcnb_push_consumed(self.ctx.h))
+
+    def _conv_begin(self, x, K, whole=False, pushed=False):
         """Start moving the dense operand ``x`` (n_pad x ld, this rank's rows) of a graph convolution to the ranks that
         need it.  No-op on a single GPU.  ``slice``: push this rank's rows of every column slice into the owners' panel
         buffers (NVLink stores).  ``gather``: one all-gather per column panel on the side stream."""
         if self.world == 1:
             return x
         if self.exchange == "slice":
-            col0, width, ldp = self._slice_plan(K)
-            self.ctx.call("gcnb_slice_push_f32", _ptr(x), int(x.shape[1]), self.n_loc, int(self.r0), _ptr(self.XP),
-                          C.c_void_p(col0.ctypes.data), C.c_void_p(width.ctypes.data), C.c_void_p(ldp.ctypes.data))
+            if not pushed:
+                col0, width, ldp = self._slice_plan(K)
+                self.ctx.call("gcnb_slice_push_f32", _ptr(x), int(x.shape[1]), self.n_loc, int(self.r0), _ptr(self.XP),
+                              C.c_void_p(col0.ctypes.data), C.c_void_p(width.ctypes.data), C.c_void_p(ldp.ctypes.data))
             return ("slice", int(K))
         ld = x.shape[1]
         panels = self._panels(K, ld, whole)
@@ -885,7 +938,9 @@ class Engine:
         with torch.cuda.stream(self.comm):
             for (c0, w, kc), src in zip(panels, srcs):
                 dst = self.gath.view(-1)[off * self.n_tot:(off + w) * self.n_tot].view(self.n_tot, w)
+                t0 = self._nccl_tick(self.comm)
                 torch.distributed.all_gather_into_tensor(dst, src, group=self.group)
+                self._nccl_tock(t0, self.comm)
                 ev = torch.cuda.Event()
                 ev.record(self.comm)
                 handle.append((dst, ev, c0, w, kc))
@@ -918,9 +973,9 @@ class Engine:
             self._spmm(csr, dst, w, C.c_void_p(out.data_ptr() + 4 * c0), ldo, kc, bias=b, act=act, softmax=softmax,
                        logits=logits)
 
-    def _conv(self, x, csr, out, ldo, K, **epi):
+    def _conv(self, x, csr, out, ldo, K, pushed=False, **epi):
         whole = bool(epi.get("softmax"))  # a row softmax needs every column of the row in one pass
-        self._conv_finish(self._conv_begin(x, K, whole), csr, out, ldo, K, **epi)
+        self._conv_finish(self._conv_begin(x, K, whole, pushed), csr, out, ldo, K, **epi)
 
     def conv_touched_bytes(self, K):
         """B_touch of one A_hat . H product of this rank: all columns of its rows, or -- feature-sliced --
@@ -958,8 +1013,11 @@ class Engine:
             self.ctx.call("gcnb_gather_rows_f32", W0, ldw0, _ptr(self.hot_idx), self.kh, hd, _ptr(self.W0_hot),
                           self.ldh[0])
             self._gemm(0, 0, n, hd, self.kh, self.X_hot, self.kh, self.W0_hot, self.ldh[0], self.H0, self.ldh[0])
+        # a highway layer convolves H0 itself (S = A.H0): its column slices leave from this kernel's epilogue
+        armed = self._arm_push(hd) if (L.layers and L.layers[0]["kind"] == "hw") else False
         self._spmm(self.X, W0, ldw0, self.H0, self.ldh[0], hd, bias=b0, act=self.act, dropout_p=p, seed=seed,
                    accumulate=2 if self.kh else 0)
+        x_pushed = self._push_done(armed)
         x, ldx, width = self.H0, self.ldh[0], hd
         self._wait_upload("A")
         for i, l in enumerate(L.layers):
@@ -972,7 +1030,8 @@ class Engine:
                 Wt, ldwt = self._pptr("Wt%d" % k)
                 bt, _ = self._pptr("bt%d" % k)
                 S = self.S.view(-1)[: self.nbuf * ldx].view(self.nbuf, ldx)
-                self._conv(x, self.A, S, ldx, width)
+                self._conv(x, self.A, S, ldx, width, pushed=x_pushed)
+                x_pushed = False
                 self.ctx.call("gcnb_highway_fwd_f32", n, width, _ptr(S), ldx, _ptr(x), ldx, Wh, ldwh, bh, Wt, ldwt,
                               bt, self.act, _ptr(b["Y"]), ldy, _ptr(b["H"]), ldy, _ptr(b["T"]), ldy)
             else:
@@ -1001,10 +1060,18 @@ class Engine:
         n = self.n_loc
         Cn = L.output_size
         csrT = self.A if self.AT is None else self.AT
-        self.ctx.call("gcnb_xent_grad_f32", _ptr(self.P), self.ldc, Cn, self.nbuf, _ptr(d_idx), _ptr(d_lab),
-                      n_idx_local, 1.0 / float(n_train_global), _ptr(self.G), self.ldc)
+        row_label = self._row_labels.get(d_idx.data_ptr())
+        pushed = False
+        if row_label is not None:  # one pass over G, column slices pushed from the same kernel in sliced runs
+            armed = self._arm_push(Cn)
+            self.ctx.call("gcnb_xent_grad_dense_f32", _ptr(self.P), self.ldc, Cn, n, _ptr(row_label),
+                          1.0 / float(n_train_global), _ptr(self.G), self.ldc)
+            pushed = self._push_done(armed)
+        else:
+            self.ctx.call("gcnb_xent_grad_f32", _ptr(self.P), self.ldc, Cn, self.nbuf, _ptr(d_idx), _ptr(d_lab),
+                          n_idx_local, 1.0 / float(n_train_global), _ptr(self.G), self.ldc)
         U = self.U.view(-1)[: self.nbuf * self.ldc].view(self.nbuf, self.ldc)
-        pending = self._conv_begin(self.G, Cn)
+        pending = self._conv_begin(self.G, Cn, pushed=pushed)
         x, ldx, width = self.x_last, self.ld_last, self.w_last
         gb, _ = self._gptr("bout")
         self.ctx.call("gcnb_colsum_f32", n, Cn, _ptr(self.G), self.ldc, gb, 0)  # dbout (overlaps the exchange)
@@ -1030,9 +1097,10 @@ class Engine:
                 gWt, ldgt = self._gptr("Wt%d" % k)
                 gbt, _ = self._gptr("bt%d" % k)
                 # dHpre, dTpre, dx*(1-t) (in place over dX) and both bias gradients in one pass
+                armed = self._arm_push(n_out)  # sliced runs: dHpre goes to its column owners, not to local memory
                 self.ctx.call("gcnb_highway_bwd_bias_f32", n, n_out, ldy, _ptr(dX), _ptr(xin), _ptr(b["H"]),
                               _ptr(b["T"]), self.act, _ptr(dH), _ptr(dT), _ptr(dX), gbh, gbt)
-                pending = self._conv_begin(dH, n_out)
+                pending = self._conv_begin(dH, n_out, pushed=self._push_done(armed))
                 V = self.U.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
                 Wh, ldwh = self._pptr("Wh%d" % k)
                 Wt, ldwt = self._pptr("Wt%d" % k)
@@ -1051,9 +1119,10 @@ class Engine:
             else:
                 dP = self.dH.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
                 gb, _ = self._gptr("b%d" % k)
+                armed = self._arm_push(n_out)
                 self.ctx.call("gcnb_act_bwd_bias_f32", n, n_out, ldy, _ptr(dX), _ptr(b["Y"]), self.act, 0.0, 0, 0,
                               _ptr(dP), gb)
-                pending = self._conv_begin(dP, n_out)
+                pending = self._conv_begin(dP, n_out, pushed=self._push_done(armed))
                 V = self.U.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
                 self._conv_finish(pending, csrT, V, ldy, n_out)
                 gW, ldgw = self._gptr("W%d" % k)
@@ -1078,7 +1147,9 @@ class Engine:
                           gW0, ldg0)
         if self.world > 1:
             with torch.cuda.stream(self.stream):
+                t0 = self._nccl_tick(self.stream)
                 torch.distributed.all_reduce(self.grads, group=self.group)
+                self._nccl_tock(t0, self.stream)
         if self.regul_coef > 0:
             reg = C.c_void_p(self.metrics.data_ptr() + 4 * 4)
             for off, size in L.weight_segments():
@@ -1162,6 +1233,35 @@ class Engine:
         self.ctx.call("gcnb_d2h", C.c_void_p(host.ctypes.data), _ptr(buf), host.nbytes)
         self.ctx.sync()
         return np.ascontiguousarray(host[:rows, :cols])
+
+    def read_rows(self, buf, rows, cols):
+        """Rows ``rows`` (global node ids) of a row-partitioned device matrix -> host (len(rows) x cols).  Collective
+        when world > 1 (the row blocks are gathered on the device; only the selected rows cross PCIe).  Checker /
+        diagnostics path (bench.py's in-run parity block), not part of the training step."""
+        if self.world > 1:
+            full = torch.empty((self.n_tot, buf.shape[1]), dtype=torch.float32, device=self.dev)
+            with torch.cuda.stream(self.stream):
+                torch.distributed.all_gather_into_tensor(full, buf.contiguous(), group=self.group)
+            buf = full
+        self.ctx.sync()
+        idx = torch.as_tensor(np.asarray(rows, dtype=np.int64), device=self.dev)
+        with torch.cuda.stream(self.stream):
+            sel = buf.index_select(0, idx)[:, :cols].contiguous()
+        self.ctx.sync()
+        return sel.cpu().numpy()
+
+    def checksum(self, buf, rows, cols):
+        """Order-independent checksum of the bit patterns of buf[:rows, :cols], summed over the ranks: equal on 1 and on
+        P GPUs exactly when the row-partitioned result is bit-identical to the single-GPU one."""
+        self.ctx.sync()
+        with torch.cuda.stream(self.stream):
+            bits = buf[:rows, :cols].contiguous().view(torch.int32).to(torch.int64)
+            mixed = (bits * 2654435761 + (bits >> 7)) & 0x7FFFFFFFFFFF
+            tot = mixed.sum().reshape(1)
+            if self.world > 1:
+                torch.distributed.all_reduce(tot, group=self.group)
+        self.ctx.sync()
+        return int(tot.item()) & 0xFFFFFFFFFFFF
 
     def gates(self):
         """Gate activations T_i of the last forward, one N x Hd array per highway layer."""

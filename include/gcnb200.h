@@ -56,8 +56,9 @@ enum gcnb_tag {
   GCNB_TAG_ADAM = 6,    /* lasagne.updates.adam (gcnmodel.py:407) */
   GCNB_TAG_COPY = 7,    /* host<->device copies issued through this ABI */
   GCNB_TAG_SPMM_A_NARROW = 8, /* A_hat . (x Wout) and its gradient: K = classes, not the hidden width */
-  GCNB_TAG_COMM = 9,    /* multi-GPU exchange kernels of this library: slice pushes and peer barriers */
-  GCNB_NTAGS = 10
+  GCNB_TAG_COMM = 9,    /* multi-GPU exchange kernels of this library: slice pushes (rows -> column slices) */
+  GCNB_TAG_SYNC = 10,   /* peer barriers: launch + flag round trip + waiting for the slowest rank */
+  GCNB_NTAGS = 11
 };
 
 /* ---------------------------------------------------------------- context ------------- */
@@ -74,7 +75,8 @@ int gcnb_set_workspace(gcnb_ctx* ctx, void* dev_ptr, size_t bytes);
  * default cache policy, 1 = L2 evict_last hint (default), 2 = evict_last with L1 allocation),
  * "spmm_unroll" (nonzeros gathered per batch), "gemm_tc" (1 = tcgen05 path where supported, the
  * default), "tc_launches" (read-only count of tcgen05 kernels launched), "sm_margin" (SMs the persistent
- * SpMM kernel leaves to concurrently running collectives). */
+ * SpMM kernel leaves to concurrently running collectives), "prof_mask" (bit t set: ops of gcnb_tag t are timed while
+ * profiling is on; default all), "peer_timeout_s" (gcnb_peer_barrier). */
 int gcnb_set_option(gcnb_ctx* ctx, const char* name, int value);
 int gcnb_get_option(const gcnb_ctx* ctx, const char* name, int* value);
 int gcnb_sync(gcnb_ctx* ctx);
@@ -233,6 +235,11 @@ int gcnb_xent_metrics_f32(gcnb_ctx* ctx, const float* P, int32_t ldp, int32_t n_
 int gcnb_xent_grad_f32(gcnb_ctx* ctx, const float* P, int32_t ldp, int32_t n_classes,
                        int32_t n_rows, const int32_t* idx, const int32_t* labels, int32_t n_idx,
                        float inv_n, float* G, int32_t ldg);
+/* the same gradient from a dense label map: row_label[r] (device int32, n_rows entries) = class of row r when r is a
+ * training row, -1 otherwise (each training row counted once).  One pass writes every row of G; when a push is armed
+ * (gcnb_push_arm) the rows also go to the owners of their columns for the graph convolution A^T.G that follows. */
+int gcnb_xent_grad_dense_f32(gcnb_ctx* ctx, const float* P, int32_t ldp, int32_t n_classes, int32_t n_rows,
+                             const int32_t* row_label, float inv_n, float* G, int32_t ldg);
 /* preds[i] = argmax P[idx[i], :] (int64), probs[i, :] = P[idx[i], :] packed n_idx x n_classes
  * f_val outputs: gcnmodel.py:393-394,411. */
 int gcnb_gather_argmax_f32(gcnb_ctx* ctx, const float* P, int32_t ldp, int32_t n_classes,
@@ -307,6 +314,16 @@ int gcnb_peer_barrier(gcnb_ctx* ctx);
  * q's panel buffer.  col0 / width / ldp: host arrays of world entries, multiples of 4. */
 int gcnb_slice_push_f32(gcnb_ctx* ctx, const float* x, int32_t ldx, int32_t n_loc, int64_t row0, float* xp_local,
                         const int32_t* col0, const int32_t* width, const int32_t* ldp);
+/* Fused push: arm the context with a slice plan (same arguments as gcnb_slice_push_f32; K = operand width).  The NEXT
+ * producer call whose output has K columns -- gcnb_spmm_csr_f32 (C, besides the local store), gcnb_highway_bwd_bias_f32
+ * (dHpre, INSTEAD of the local store), gcnb_act_bwd_bias_f32 (dZ, besides), gcnb_xent_grad_dense_f32 (G, besides) --
+ * stores that output straight into the owners' panel buffers from its own epilogue, so the transfer rides under the
+ * producer's HBM traffic and gcnb_slice_push_f32 is not needed.  gcnb_push_consumed returns 1 if a producer did so
+ * since arming (0: call gcnb_slice_push_f32) and disarms.  GCNB_E_UNSUPPORTED for K > 1024. */
+int gcnb_push_arm(gcnb_ctx* ctx, float* xp_local, int32_t K, const int32_t* col0, const int32_t* width,
+                  const int32_t* ldp, int64_t row0);
+int gcnb_push_consumed(gcnb_ctx* ctx);
+
 /* The sliced product: C[:, col0 : col0 + width] = epilogue(A . XP[:, 0 : width]) for ALL rows of A (the replicated
  * A_hat, n_rows = N); row i is stored into rank (i / n_pad)'s copy of C at local row i % n_pad.  `C` is this rank's
  * address of the output inside the arena (ldc floats per row, K = logical width of the whole operand for the
