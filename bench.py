@@ -232,7 +232,13 @@ def run_gpu(args, cfg, wname):
     t_gen = time.time()
     # each rank generates the rows of X it owns (rows outside its block stay empty)
     rr = row_blocks(cfg["n"], world)[1][rank] if world > 1 else None
-    A, X, Y, tr, dev, te, _ = synth.synthetic_problem(cfg, seed=77, alpha=args.alpha, row_range=rr)
+    # A_hat comes out of the library's GPU builder (csrc/adjacency.cu; bit-identical to the NumPy restatement of
+    # gcnmain.py:115-128, tests/test_gpu_adjacency.py) -- the host np.unique over 2 x 63M edge keys of C4 takes minutes
+    from geographconv_b200 import adjacency
+    A, X, Y, tr, dev, te, _ = synth.synthetic_problem(
+        cfg, seed=77, alpha=args.alpha, row_range=rr,
+        graph_builder=None if args.host_graph else
+        (lambda u, v, n: adjacency.normalized_adjacency_from_edges(u, v, n, device=local_rank)))
     t_gen = time.time() - t_gen
     N = cfg["n"]
     clf = GraphConv(cfg["f"], cfg["classes"], cfg["hid"], regul_coef=0.0, drop_out=0.5, highway=True,
@@ -245,7 +251,7 @@ def run_gpu(args, cfg, wname):
         eng.ctx.set_option("gemm_tc", args.gemm_tc)
     y_tr, y_dev = Y[tr], Y[dev]
     t_bind = time.time()
-    eng.bind(X, A, need_backward=True)
+    eng.bind(X, A, need_backward=True, assume_symmetric=True)  # symmetric by construction (synth.synthetic_graph)
     d_tr = eng.index_arrays(tr, y_tr)
     d_dev = eng.index_arrays(dev, y_dev)
     eng.ctx.sync()
@@ -261,6 +267,7 @@ def run_gpu(args, cfg, wname):
 
     hd = cfg["hid"][0]
     # ---- in-run parity block (initial weights; before anything is trained) ----
+    barrier()  # host preparation takes a different time on every rank; the device barriers of the step are short-fused
     parity = parity_block(eng, clf, A, cfg, rank, args.parity_rows) if args.parity_rows > 0 else None
 
     # ---- device-resident leg (value) ----
@@ -444,7 +451,8 @@ def capi_tag(name):
 def parity_block(eng, clf, A, cfg, rank, n_rows):
     """In-run parity (every N; collective): one forward pass with the initial weights and a fixed dropout seed, then
     * ``forward_checksum``: checksum of the bit patterns of all N x C probabilities (identical at every GPU count iff the
-      row-partitioned forward is bit-identical to the single-GPU forward);
+      row-partitioned forward is bit-identical to the single-GPU forward); ``spmm_checksum``: the same over all of
+      S = A_hat.H0 (identical across SpMM engines and exchange designs iff they agree bit for bit);
     * ``spmm``: ``n_rows`` sampled rows of S = A_hat.H0 recomputed in float64 with SciPy from the device's own H0 rows;
     * ``probs``: the same rows of P = softmax(A_hat.(Y.Wout) + bout) recomputed in float64 from the device's own last
       hidden layer Y; argmax compared on every sampled row.
@@ -464,6 +472,7 @@ def parity_block(eng, clf, A, cfg, rank, n_rows):
     # (1) one A_hat.H product through the engine's exchange path: S = A_hat.H0
     S = eng.S.view(-1)[: eng.nbuf * eng.ldh[0]].view(eng.nbuf, eng.ldh[0])
     eng._conv(eng.H0, eng.A, S, eng.ldh[0], hd)
+    spmm_checksum = eng.checksum(S, eng.n_loc, hd)
     s_gpu = eng.read_rows(S, rows, hd)
     h0_nb = eng.read_rows(eng.H0, nb, hd)
     # (2) final probabilities from the device's own last hidden layer
@@ -483,6 +492,7 @@ def parity_block(eng, clf, A, cfg, rank, n_rows):
         mism = np.nonzero(p_gpu.argmax(1) != p_ref.argmax(1))[0]
         top2 = np.sort(p_ref[mism], axis=1)[:, -2:] if len(mism) else np.zeros((0, 2))
         out = {"rows_sampled": int(len(rows)), "forward_checksum": "%012x" % checksum,
+               "spmm_checksum": "%012x" % spmm_checksum,
                "spmm_max_rel": spmm_err, "probs_max_rel": probs_err, "max_rel": max(spmm_err, probs_err),
                "argmax_mismatch": int(len(mism)),
                "argmax_mismatch_top2_rel_gap": [float((b - a) / b) for a, b in top2],
@@ -519,6 +529,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample-nodes", type=int, default=32768)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--host-graph", action="store_true", help="build A_hat with the NumPy restatement instead of the GPU builder")
     ap.add_argument("--no-cpu-full-ops", action="store_true", help="skip the full-size host SpMM / GEMM timing")
     ap.add_argument("--parity-rows", type=int, default=2000, help="rows of the in-run parity block (0 = skip)")
     ap.add_argument("--ncu-traffic-bytes", type=float, default=None,

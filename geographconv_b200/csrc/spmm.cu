@@ -975,7 +975,9 @@ extern "C" int gcnb_spmm_csr_sliced_f32(gcnb_ctx* ctx, const gcnb_csr* A, const 
   if (epi) {
     p.bias = epi->bias; p.act = epi->act;
   }
-  return launch_panels(ctx, p, A->n_rows, width, ctx->spmm_unroll, true);
+  // panel width: the context's "spmm_panel" option (32 unless set: 64 gathers 256-byte rows, for operands whose
+  // 128-byte panel no longer fits L2)
+  return launch_panels(ctx, p, A->n_rows, width, ctx->spmm_unroll, false);
 }
 
 extern "C" int gcnb_row_softmax_f32(gcnb_ctx* ctx, float* C, int32_t ldc, int32_t n_rows, int32_t K, float* logits) {

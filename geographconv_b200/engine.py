@@ -503,6 +503,8 @@ class Engine:
                     import logging
                     logging.warning("NVLink peer memory unavailable (%s): using the all-gather exchange", e)
                     self.exchange = "gather"
+        if "GCNB_SPMM_PANEL" in os.environ:  # column-panel width of the panel engine (16 / 32 / 64 floats)
+            self.ctx.set_option("spmm_panel", int(os.environ["GCNB_SPMM_PANEL"]))
         if self.world > 1 and "GCNB_SM_MARGIN" in os.environ:
             # SMs the persistent SpMM kernel leaves to concurrently running NCCL kernels
             self.ctx.set_option("sm_margin", int(os.environ["GCNB_SM_MARGIN"]))

@@ -53,11 +53,14 @@ def normalized_adjacency_from_edges(u, v, n, dtype=np.float32):
     return A
 
 
-def synthetic_graph(n, avg_degree, seed=77, alpha=None):
+def synthetic_graph(n, avg_degree, seed=77, alpha=None, builder=None):
     """A_hat for a random undirected graph with about ``avg_degree`` nonzeros per row.
 
     ``alpha=None``: endpoints uniform.  Otherwise Chung-Lu endpoints with weights
     w_i ~ i^(-1/(alpha-1)) (power-law degree exponent ``alpha``; BASELINE.json configs[4]).
+    ``builder(u, v, n)``: what turns the edge list into A_hat -- default the NumPy restatement of
+    gcnmain.py:115-128 below; ``geographconv_b200.adjacency.normalized_adjacency_from_edges`` builds
+    the bit-identical matrix on the GPU (seconds instead of minutes at N = 2M, degree 64).
     """
     rng = np.random.RandomState(seed)
     m = max(int(n * max(avg_degree - 1, 0) / 2), 0)
@@ -71,7 +74,7 @@ def synthetic_graph(n, avg_degree, seed=77, alpha=None):
         perm = rng.permutation(n)  # hubs are not the first rows
         u = perm[np.minimum(np.searchsorted(cdf, rng.random_sample(m)), n - 1)]
         v = perm[np.minimum(np.searchsorted(cdf, rng.random_sample(m)), n - 1)]
-    return normalized_adjacency_from_edges(u, v, n)
+    return (builder or normalized_adjacency_from_edges)(u, v, n)
 
 
 def _zipf_draws_for_unique(p, target):
@@ -158,12 +161,12 @@ def split_indices(n):
     return idx[:n_tr], idx[n_tr:n_tr + n_dev], idx[n_tr + n_dev:]
 
 
-def synthetic_problem(name_or_cfg, seed=77, alpha=None, row_range=None):
+def synthetic_problem(name_or_cfg, seed=77, alpha=None, row_range=None, graph_builder=None):
     """(A_hat, X, Y, train_idx, dev_idx, test_idx, cfg) for one of ``CONFIGS`` or a cfg dict.
     ``row_range`` = (r0, r1): generate only those rows of X (others empty) -- what one rank of a
-    row-partitioned run needs."""
+    row-partitioned run needs.  ``graph_builder``: see ``synthetic_graph``."""
     cfg = dict(CONFIGS[name_or_cfg]) if isinstance(name_or_cfg, str) else dict(name_or_cfg)
-    A = synthetic_graph(cfg["n"], cfg["deg"], seed, alpha)
+    A = synthetic_graph(cfg["n"], cfg["deg"], seed, alpha, builder=graph_builder)
     X = synthetic_features(cfg["n"], cfg["f"], cfg["xnnz"], seed, row_range=row_range)
     Y = synthetic_labels(cfg["n"], cfg["classes"], seed)
     tr, dev, te = split_indices(cfg["n"])
