@@ -63,6 +63,7 @@ SIGNATURES = {
     "gcnb_d2h": (C.c_int, [_ctxp, _vp, _vp, _sz]),
     "gcnb_memset": (C.c_int, [_ctxp, _vp, C.c_int, _sz]),
     "gcnb_copy2d_f32": (C.c_int, [_ctxp, _vp, _i32, _vp, _i32, _i32, _i32]),
+    "gcnb_expand_u16_i32": (C.c_int, [_ctxp, _vp, _i64, _vp]),
     "gcnb_csr_plan": (C.c_int, [_vp, _i32, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), _vp, _vp]),
     "gcnb_spmm_csr_f32": (C.c_int, [_ctxp, C.POINTER(GcnbCsr), _vp, _i32, _vp, _i32, _i32, C.POINTER(GcnbEpilogue)]),
     "gcnb_spmm_engine_for": (C.c_int, [_ctxp, C.POINTER(GcnbCsr), _i32, _i32]),

@@ -13,8 +13,12 @@
 //                 inside a bucket is arbitrary and is erased by the next step)
 //   4. sort       each bucket is sorted in place: a warp per bucket in shared memory (<= 128 entries) or a CTA per
 //                 bucket in shared memory (<= 4096) with an all-ascending ("flip") bitonic network; hubs of
-//                 power-law graphs (> 4096 entries) go through an n-bit presence bitmap instead (set, then
-//                 enumerate in order: O(n/32 + m) instead of O(m log^2 m)); distinct entries are counted
+//                 power-law graphs (> 4096 entries, up to most of the edge list at alpha = 1.5) go through an n-bit
+//                 presence bitmap instead: the whole grid sets the bits of a batch of hub buckets (blockIdx.y = hub),
+//                 then one CTA per hub enumerates the set bits in ascending order -- O(n/32 + m) instead of
+//                 O(m log^2 m), and the result holds the DISTINCT neighbours only; distinct entries are counted.
+//                 Count and scatter aggregate their atomics per warp (__match_any_sync), so that a hub that owns 60%
+//                 of the edge ends costs one atomic per warp, not one per edge end.
 //   5. scan       distinct counts -> rowptr of A_hat
 //   6. fill       distinct neighbours are compacted into colidx (ascending inside a row) and
 //                 val = float32( (d_i * 1.0) * d_j ) with d = 1/sqrt(double(row nnz)): the float64 arithmetic and
@@ -37,10 +41,12 @@ constexpr int kBigCtas = 128;     // CTAs of the big-bucket kernel (each owns on
 struct AdjWork {  // carved out of the caller's workspace (all 256-byte aligned)
   int* cnt;       // n+1: raw bucket sizes, later reused for the distinct counts
   int* rawptr;    // n+1
-  int* cursor;    // n
-  int* biglist;   // n
+  int* cursor;    // n: slot cursor during the scatter, afterwards the effective bucket length (efflen: the sorted
+                  //    length, or -distinct for a hub bucket that was compacted through the bitmap)
+  int* biglist;   // n: buckets of more than 128 entries
+  int* hublist;   // n: of those, the ones of more than 4096 entries
   int* tmp;       // scan block sums
-  int* flags;     // [0] out-of-range edge seen, [1] number of big buckets
+  int* flags;     // [0] out-of-range edge seen, [1] number of big buckets, [2] number of hubs
   double* dinv;   // n
   unsigned* bitmaps;  // kBigCtas x ceil(n / 32)
   int* raw;       // 2E + n
@@ -61,12 +67,13 @@ __host__ size_t carve(AdjWork* w, char* base, long long n_edges, int n) {
   int* rawptr = (int*)take(n1 * 4);
   int* cursor = (int*)take(n1 * 4);
   int* biglist = (int*)take(n1 * 4);
+  int* hublist = (int*)take(n1 * 4);
   int* tmp = (int*)take(nblocks * 4);
   int* flags = (int*)take(256);
   double* dinv = (double*)take(n1 * 8);
   unsigned* bitmaps = (unsigned*)take((size_t)kBigCtas * ((n1 + 31) / 32) * 4);
   int* raw = (int*)take(((size_t)2 * (size_t)n_edges + n1) * 4);
-  if (w) *w = AdjWork{cnt, rawptr, cursor, biglist, tmp, flags, dinv, bitmaps, raw};
+  if (w) *w = AdjWork{cnt, rawptr, cursor, biglist, hublist, tmp, flags, dinv, bitmaps, raw};
   return off;
 }
 
@@ -177,6 +184,25 @@ __global__ void adj_init(int* cnt, int* cursor, int n) {
   }
 }
 
+// warp-aggregated counter updates: the lanes that hit the same node elect a leader that adds their count once.
+// Called under divergence (invalid / self-loop edges skip it): the group is formed among the lanes that are here.
+__device__ __forceinline__ void agg_add(int* cnt, int node) {
+  const unsigned active = __activemask();
+  const unsigned peers = __match_any_sync(active, node);
+  if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(cnt + node, __popc(peers));
+}
+// the same for slot allocation: returns this lane's slot in the bucket of `node`
+__device__ __forceinline__ int agg_slot(int* cursor, int node) {
+  const unsigned active = __activemask();
+  const unsigned peers = __match_any_sync(active, node);
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(peers) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(cursor + node, __popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  return base + __popc(peers & ((1u << lane) - 1u));
+}
+
 __global__ void adj_count(const int* __restrict__ u, const int* __restrict__ v, long long n_edges, int n, int* cnt,
                           int* flags) {
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -187,8 +213,8 @@ __global__ void adj_count(const int* __restrict__ u, const int* __restrict__ v, 
       continue;
     }
     if (a == b) continue;  // setdiag(0): existing self loops are replaced by the unit one
-    atomicAdd(cnt + a, 1);
-    atomicAdd(cnt + b, 1);
+    agg_add(cnt, a);
+    agg_add(cnt, b);
   }
 }
 
@@ -203,8 +229,8 @@ __global__ void adj_scatter(const int* __restrict__ u, const int* __restrict__ v
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += stride) {
     const int a = u[e], b = v[e];
     if (a < 0 || a >= n || b < 0 || b >= n || a == b) continue;
-    raw[rawptr[a] + atomicAdd(cursor + a, 1)] = b;
-    raw[rawptr[b] + atomicAdd(cursor + b, 1)] = a;
+    raw[rawptr[a] + agg_slot(cursor, a)] = b;
+    raw[rawptr[b] + agg_slot(cursor, b)] = a;
   }
 }
 
@@ -260,7 +286,7 @@ __device__ __forceinline__ int warp_count_distinct(const int* a, int m, int lane
 }
 
 __global__ void __launch_bounds__(256) adj_sort_small(const int* __restrict__ rawptr, int* raw, int n, int* distinct,
-                                                      int* biglist, int* flags) {
+                                                      int* efflen, int* biglist, int* flags) {
   __shared__ int buf[8][kWarpRowMax];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = blockIdx.x * 8 + warp;
@@ -276,73 +302,121 @@ __global__ void __launch_bounds__(256) adj_sort_small(const int* __restrict__ ra
   bitonic_flip_sort(a, m, lane, 32, [] { __syncwarp(); });
   for (int i = lane; i < m; i += 32) raw[b + i] = a[i];
   const int d = warp_count_distinct(a, m, lane);
-  if (lane == 0) distinct[r] = d;
+  if (lane == 0) {
+    distinct[r] = d;
+    efflen[r] = m;  // sorted, duplicates still in place
+  }
 }
 
+// buckets of 129 .. 4096 entries: a CTA sorts them in shared memory; larger ones ("hubs") are queued for the bitmap path
 __global__ void __launch_bounds__(kSortThreads) adj_sort_big(const int* __restrict__ rawptr, int* raw, int* distinct,
-                                                             const int* __restrict__ biglist, const int* flags, int n,
-                                                             unsigned* bitmaps) {
+                                                             int* efflen, const int* __restrict__ biglist, int* flags,
+                                                             int* hublist) {
   __shared__ int buf[kCtaRowMax];
-  __shared__ int wtot[kSortThreads / 32];
   const int nbig = flags[1];
-  const int words = (n + 31) >> 5;
-  unsigned* bm = bitmaps + (size_t)blockIdx.x * (size_t)(((size_t)n + 1 + 31) / 32);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   for (int q = blockIdx.x; q < nbig; q += gridDim.x) {
     const int r = biglist[q];
     const int b = rawptr[r], m = rawptr[r + 1] - b;
     int* a = raw + b;
-    if (m <= kCtaRowMax) {
-      for (int i = tid; i < m; i += kSortThreads) buf[i] = a[i];
-      __syncthreads();
-      bitonic_flip_sort(buf, m, tid, kSortThreads, [] { __syncthreads(); });
-      for (int i = tid; i < m; i += kSortThreads) a[i] = buf[i];
-      __syncthreads();
-      if (tid < 32) {
-        const int d = warp_count_distinct(a, m, tid);
-        if (tid == 0) distinct[r] = d;
+    if (m > kCtaRowMax) {
+      if (tid == 0) hublist[atomicAdd(flags + 2, 1)] = r;
+      continue;
+    }
+    for (int i = tid; i < m; i += kSortThreads) buf[i] = a[i];
+    __syncthreads();
+    bitonic_flip_sort(buf, m, tid, kSortThreads, [] { __syncthreads(); });
+    for (int i = tid; i < m; i += kSortThreads) a[i] = buf[i];
+    __syncthreads();
+    if (tid < 32) {
+      const int d = warp_count_distinct(a, m, tid);
+      if (tid == 0) {
+        distinct[r] = d;
+        efflen[r] = m;
       }
-    } else {
-      // presence bitmap over the node ids, then the set bits in ascending order are the sorted distinct neighbours;
-      // the tail of the bucket repeats the largest one so that the bucket stays "sorted with duplicates"
-      for (int i = tid; i < words; i += kSortThreads) bm[i] = 0u;
-      __syncthreads();
-      for (int i = tid; i < m; i += kSortThreads) {
-        const int x = a[i];
-        atomicOr(bm + (x >> 5), 1u << (x & 31));
-      }
-      __syncthreads();
-      const int per = (words + kSortThreads - 1) / kSortThreads;
-      const int w0 = min(tid * per, words), w1 = min(w0 + per, words);
-      int c = 0;
-      for (int w = w0; w < w1; ++w) c += __popc(bm[w]);
-      int x = c;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x += y;
-      }
-      if (lane == 31) wtot[warp] = x;
-      __syncthreads();
-      int off = x - c, d = 0;
-      for (int w = 0; w < kSortThreads / 32; ++w) {
-        if (w < warp) off += wtot[w];
-        d += wtot[w];
-      }
-      for (int w = w0; w < w1; ++w) {
-        unsigned bits = bm[w];
-        while (bits) {
-          const int t = __ffs(bits) - 1;
-          bits &= bits - 1;
-          a[off++] = (w << 5) | t;
-        }
-      }
-      __syncthreads();
-      const int last = a[d - 1];
-      for (int i = d + tid; i < m; i += kSortThreads) a[i] = last;
-      if (tid == 0) distinct[r] = d;
     }
     __syncthreads();
+  }
+}
+
+// hubs, step 1: the whole grid sets presence bits.  blockIdx.y = hub of this batch (its own n-bit bitmap, zeroed before),
+// blockIdx.x strides over the hub's raw bucket.  Neighbour ids spread over the bitmap words, so the RED.OR traffic of a
+// 9M-entry bucket is spread over every SM and L2 slice instead of queueing behind one CTA.
+__global__ void __launch_bounds__(256) adj_hub_setbits(const int* __restrict__ rawptr, const int* __restrict__ raw,
+                                                       const int* __restrict__ hublist, const int* flags, int batch0,
+                                                       size_t bm_words, unsigned* bitmaps) {
+  const int h = batch0 + blockIdx.y;
+  if (h >= flags[2]) return;
+  const int r = hublist[h];
+  const int b = rawptr[r], m = rawptr[r + 1] - b;
+  unsigned* bm = bitmaps + (size_t)blockIdx.y * bm_words;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
+    const int x = raw[b + i];
+    atomicOr(bm + (x >> 5), 1u << (x & 31));
+  }
+}
+
+// hubs, step 2: one CTA per hub turns the bitmap into the ascending list of DISTINCT neighbours at the head of the
+// bucket (a thread owns a contiguous range of words: popcount, block scan, enumerate).  efflen = -d marks the bucket as
+// compacted: adj_fill_hubs copies it with the whole grid, the warp-per-row fill skips it.
+__global__ void __launch_bounds__(kSortThreads) adj_hub_enumerate(const int* __restrict__ rawptr, int* raw, int* distinct,
+                                                                  int* efflen, const int* __restrict__ hublist,
+                                                                  const int* flags, int batch0, int n, size_t bm_words,
+                                                                  const unsigned* __restrict__ bitmaps) {
+  __shared__ int wtot[kSortThreads / 32];
+  const int h = batch0 + blockIdx.x;
+  if (h >= flags[2]) return;
+  const int r = hublist[h];
+  int* a = raw + rawptr[r];
+  const unsigned* bm = bitmaps + (size_t)blockIdx.x * bm_words;
+  const int words = (n + 31) >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (words + kSortThreads - 1) / kSortThreads;
+  const int w0 = min(tid * per, words), w1 = min(w0 + per, words);
+  int c = 0;
+  for (int w = w0; w < w1; ++w) c += __popc(bm[w]);
+  int x = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) wtot[warp] = x;
+  __syncthreads();
+  int off = x - c, d = 0;
+  for (int w = 0; w < kSortThreads / 32; ++w) {
+    if (w < warp) off += wtot[w];
+    d += wtot[w];
+  }
+  for (int w = w0; w < w1; ++w) {
+    unsigned bits = bm[w];
+    while (bits) {
+      const int t = __ffs(bits) - 1;
+      bits &= bits - 1;
+      a[off++] = (w << 5) | t;
+    }
+  }
+  if (tid == 0) {
+    distinct[r] = d;
+    efflen[r] = -d;
+  }
+}
+
+// hubs, step 3 (after rowptr is known): entries are distinct and ascending, so the fill is a parallel copy + scale
+__global__ void __launch_bounds__(256) adj_fill_hubs(const int* __restrict__ rawptr, const int* __restrict__ raw,
+                                                     const int* __restrict__ rowptr, const double* __restrict__ dinv,
+                                                     const int* __restrict__ hublist, const int* flags,
+                                                     int* __restrict__ colidx, float* __restrict__ val) {
+  const int h = blockIdx.y;
+  if (h >= flags[2]) return;
+  const int r = hublist[h];
+  const int* a = raw + rawptr[r];
+  const int out = rowptr[r], d = rowptr[r + 1] - out;
+  const double di = dinv[r];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d; i += gridDim.x * blockDim.x) {
+    const int x = a[i];
+    colidx[out + i] = x;
+    val[out + i] = (float)((di * 1.0) * dinv[x]);
   }
 }
 
@@ -356,12 +430,14 @@ __global__ void adj_dinv(const int* __restrict__ rowptr, double* dinv, int n) {
 
 // warp per row: compact the distinct neighbours, scale
 __global__ void __launch_bounds__(256) adj_fill(const int* __restrict__ rawptr, const int* __restrict__ raw,
-                                                const int* __restrict__ rowptr, const double* __restrict__ dinv, int n,
+                                                const int* __restrict__ efflen, const int* __restrict__ rowptr,
+                                                const double* __restrict__ dinv, int n,
                                                 int* __restrict__ colidx, float* __restrict__ val) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= n) return;
-  const int b = rawptr[r], m = rawptr[r + 1] - b;
+  const int b = rawptr[r], m = efflen[r];
+  if (m < 0) return;  // compacted hub: adj_fill_hubs
   const int* a = raw + b;
   const double di = dinv[r];
   int out = rowptr[r];
@@ -425,10 +501,26 @@ extern "C" int gcnb_adj_build_rows(gcnb_ctx* ctx, const int32_t* u, const int32_
   }
   if (n > 0) {
     // distinct counts overwrite the raw counts (the bucket offsets are already in rawptr)
-    adj_sort_small<<<cdiv(n, 8), 256, 0, ctx->stream>>>(w.rawptr, w.raw, n, w.cnt, w.biglist, w.flags);
+    adj_sort_small<<<cdiv(n, 8), 256, 0, ctx->stream>>>(w.rawptr, w.raw, n, w.cnt, w.cursor, w.biglist, w.flags);
     GCNB_LAUNCHED(ctx);
-    adj_sort_big<<<kBigCtas, kSortThreads, 0, ctx->stream>>>(w.rawptr, w.raw, w.cnt, w.biglist, w.flags, n, w.bitmaps);
+    adj_sort_big<<<kBigCtas, kSortThreads, 0, ctx->stream>>>(w.rawptr, w.raw, w.cnt, w.cursor, w.biglist, w.flags,
+                                                             w.hublist);
     GCNB_LAUNCHED(ctx);
+    // hubs (buckets of more than 4096 entries; none on a uniform graph): the count decides how many bitmap batches run
+    int n_hubs = 0;
+    GCNB_CUDA(ctx, cudaMemcpyAsync(&n_hubs, w.flags + 2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    GCNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const size_t bm_words = ((size_t)n + 1 + 31) / 32;
+    for (int b0 = 0; b0 < n_hubs; b0 += kBigCtas) {
+      const int nb = n_hubs - b0 < kBigCtas ? n_hubs - b0 : kBigCtas;
+      GCNB_CUDA(ctx, cudaMemsetAsync(w.bitmaps, 0, (size_t)nb * bm_words * 4, ctx->stream));
+      adj_hub_setbits<<<dim3((unsigned)(ctx->sm_count * 2), (unsigned)nb), 256, 0, ctx->stream>>>(
+          w.rawptr, w.raw, w.hublist, w.flags, b0, bm_words, w.bitmaps);
+      GCNB_LAUNCHED(ctx);
+      adj_hub_enumerate<<<nb, kSortThreads, 0, ctx->stream>>>(w.rawptr, w.raw, w.cnt, w.cursor, w.hublist, w.flags, b0, n,
+                                                              bm_words, w.bitmaps);
+      GCNB_LAUNCHED(ctx);
+    }
   }
   rc = exclusive_scan(ctx, w.cnt, rowptr, n + 1, w.tmp);
   if (rc != GCNB_OK) return rc;
@@ -456,8 +548,16 @@ extern "C" int gcnb_adj_fill_f32(gcnb_ctx* ctx, int64_t n_edges, int32_t n_nodes
   ProfScope scope(ctx, GCNB_TAG_ELEM);
   AdjWork w;
   carve(&w, const_cast<char*>(reinterpret_cast<const char*>(work)), n_edges, n_nodes);
-  adj_fill<<<cdiv(n_nodes, 8), 256, 0, ctx->stream>>>(w.rawptr, w.raw, rowptr, w.dinv, n_nodes, colidx, val);
+  adj_fill<<<cdiv(n_nodes, 8), 256, 0, ctx->stream>>>(w.rawptr, w.raw, w.cursor, rowptr, w.dinv, n_nodes, colidx, val);
   GCNB_LAUNCHED(ctx);
+  int n_hubs = 0;
+  GCNB_CUDA(ctx, cudaMemcpyAsync(&n_hubs, w.flags + 2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  GCNB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n_hubs > 0) {
+    adj_fill_hubs<<<dim3(64u, (unsigned)n_hubs), 256, 0, ctx->stream>>>(w.rawptr, w.raw, rowptr, w.dinv, w.hublist, w.flags,
+                                                                          colidx, val);
+    GCNB_LAUNCHED(ctx);
+  }
   return GCNB_OK;
 }
 

@@ -420,6 +420,20 @@ __global__ void move_rows_kernel(const float* src, int ld_src, const int* idx, i
   }
 }
 
+// column ids that fit 16 bits cross PCIe as uint16 and are widened here (8 per thread: one 128-bit load, two stores)
+__global__ void __launch_bounds__(kThreads) expand_u16_kernel(const uint16_t* __restrict__ src, long long n, int* dst) {
+  const long long n8 = n >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = reinterpret_cast<const uint4*>(src)[i];
+    int4 lo = make_int4((int)(v.x & 0xffffu), (int)(v.x >> 16), (int)(v.y & 0xffffu), (int)(v.y >> 16));
+    int4 hi = make_int4((int)(v.z & 0xffffu), (int)(v.z >> 16), (int)(v.w & 0xffffu), (int)(v.w >> 16));
+    reinterpret_cast<int4*>(dst)[2 * i] = lo;
+    reinterpret_cast<int4*>(dst)[2 * i + 1] = hi;
+  }
+  if (blockIdx.x == 0)
+    for (long long i = (n8 << 3) + threadIdx.x; i < n; i += blockDim.x) dst[i] = (int)src[i];
+}
+
 inline int grid_for(const gcnb_ctx* ctx, long long work_items) {
   long long g = (work_items + kThreads - 1) / kThreads;
   const long long cap = (long long)ctx->sm_count * 16;
@@ -717,4 +731,15 @@ extern "C" int gcnb_gather_rows_f32(gcnb_ctx* ctx, const float* src, int32_t ld_
 extern "C" int gcnb_scatter_rows_f32(gcnb_ctx* ctx, const float* src, int32_t ld_src, const int32_t* idx,
                                      int32_t n_idx, int32_t k, float* dst, int32_t ld_dst) {
   return move_rows(ctx, src, ld_src, idx, n_idx, k, dst, ld_dst, 1);
+}
+
+extern "C" int gcnb_expand_u16_i32(gcnb_ctx* ctx, const uint16_t* src, int64_t n, int32_t* dst) {
+  if (!ctx) return GCNB_E_INVALID;
+  if (n == 0) return GCNB_OK;
+  GCNB_REQUIRE(ctx, src && dst && n > 0, "null pointer");
+  GCNB_REQUIRE(ctx, aligned16(src) && aligned16(dst), "16-byte alignment");
+  ProfScope scope(ctx, GCNB_TAG_COPY);
+  expand_u16_kernel<<<grid_for(ctx, (n + 7) / 8), kThreads, 0, ctx->stream>>>(src, n, dst);
+  GCNB_LAUNCHED(ctx);
+  return GCNB_OK;
 }

@@ -160,11 +160,14 @@ class HostCsr:
         self.col_blocks = int(col_blocks)
         self.rowptr = _pinned(rowptr)
         self.colidx = _pinned(np.ascontiguousarray(M.indices, dtype=np.int32))
+        # column ids below 65536 (the BoW features) cross PCIe as uint16 and are widened on the device
+        self.colidx16 = _pinned(self.colidx.astype(np.uint16)) if (self.shape[1] <= 65536 and self.nnz) else None
         self.val = _pinned(np.ascontiguousarray(M.data, dtype=np.float32))
         self.items = _pinned(items.reshape(-1))
         self.long_rows = _pinned(long_rows.reshape(-1))
         self.n_items, self.n_long, self.n_slots = len(items), len(long_rows), int(n_slots)
-        self.nbytes = sum(a.nbytes for a in (self.rowptr, self.colidx, self.val, self.items, self.long_rows))
+        self.nbytes = sum(a.nbytes for a in (self.rowptr, self.colidx if self.colidx16 is None else self.colidx16,
+                                             self.val, self.items, self.long_rows))  # bytes one upload moves
 
 
 def split_hot_columns(Xl, min_density, max_cols, df=None, n_total=None):
@@ -188,7 +191,7 @@ def split_hot_columns(Xl, min_density, max_cols, df=None, n_total=None):
     if n_total == 0 or int(df.sum()) == 0 or max_cols < 32 or min_density <= 0:
         return None, None, Xl
     n_hot = int(np.count_nonzero(df >= min_density * n_total))
-    kh = min(n_hot, int(max_cols)) // 32 * 32
+    kh = min(n_hot, int(max_cols), 65536) // 32 * 32  # hot-local ids travel as uint16
     if kh < 64:
         return None, None, Xl
     order = np.argsort(-df, kind="stable")
@@ -260,7 +263,7 @@ class HostGraph:
         self.kh = 0 if self.hot_cols is None else len(self.hot_cols)
         self.hot_cols_p = _pinned(self.hot_cols) if self.kh else None
         self.hot_ptr = _pinned(np.ascontiguousarray(X_hot.indptr, dtype=np.int32)) if self.kh else None
-        self.hot_col = _pinned(np.ascontiguousarray(X_hot.indices, dtype=np.int32)) if self.kh else None
+        self.hot_col = _pinned(np.ascontiguousarray(X_hot.indices, dtype=np.uint16)) if self.kh else None  # kh <= 65536
         self.hot_val = _pinned(np.ascontiguousarray(X_hot.data, dtype=np.float32)) if self.kh else None
         self.X = HostCsr(Xl, chunk)  # the cold columns only when a hot block exists
         self.A = HostCsr(Al, chunk)
@@ -293,6 +296,8 @@ class DeviceCsr:
         self.t_val = torch.empty(max(host.val.size, 1), dtype=torch.float32, device=eng.dev)
         self.t_items = i32(host.items.size)
         self.t_long = i32(host.long_rows.size)
+        self.t_col16 = torch.empty(host.colidx16.size + 8, dtype=torch.int16, device=eng.dev) \
+            if host.colidx16 is not None else None
         s = GcnbCsr()
         s.n_rows, s.n_cols, s.nnz = host.shape[0], host.shape[1], host.nnz
         s.rowptr, s.colidx, s.val = self.t_rowptr.data_ptr(), self.t_colidx.data_ptr(), self.t_val.data_ptr()
@@ -311,7 +316,10 @@ class DeviceCsr:
         ctx = eng.ctx if ctx is None else ctx
         for dst, src in ((self.t_rowptr, host.rowptr), (self.t_colidx, host.colidx), (self.t_val, host.val),
                          (self.t_items, host.items), (self.t_long, host.long_rows)):
-            if src.size:
+            if src is host.colidx and self.t_col16 is not None:
+                ctx.call("gcnb_h2d", _ptr(self.t_col16), C.c_void_p(host.colidx16.ctypes.data), host.colidx16.nbytes)
+                ctx.call("gcnb_expand_u16_i32", _ptr(self.t_col16), host.colidx16.size, _ptr(self.t_colidx))
+            elif src.size:
                 ctx.call("gcnb_h2d", _ptr(dst), C.c_void_p(src.ctypes.data), src.nbytes)
 
     def retagged(self, tag):
@@ -436,6 +444,8 @@ class PeerArena:
 class Engine:
     """One GPU's share of the GCN: weights (replicated), row block of the graph, activations."""
 
+    SLICE_PANEL_BYTES_MAX = 80 << 20  # same L2 rule as the panel SpMM engine (spmm.cu pick_engine)
+
     def __init__(self, layout: ParamLayout, drop_out=0.0, regul_coef=0.0, nonlin="tanh", device=None,
                  group=None, spmm_chunk=SPMM_CHUNK_DEFAULT, keep_logits=False, hot_density=None, hot_max=None):
         if not torch.cuda.is_available():
@@ -480,17 +490,22 @@ class Engine:
         self.copy_stream = torch.cuda.Stream(self.dev)
         self.copy_ctx = capi.Context(int(device), C.c_void_p(self.copy_stream.cuda_stream))
         self._uploads = {}
-        # exchange design of the graph convolutions (module docstring); "slice" needs CUDA IPC between the ranks
-        self.exchange = os.environ.get("GCNB_EXCHANGE", "slice") if self.world > 1 else "none"
-        if self.exchange not in ("slice", "gather", "none"):
-            raise ValueError("GCNB_EXCHANGE must be 'slice' or 'gather'")
+        # exchange design of the graph convolutions (module docstring); "slice" needs CUDA IPC between the ranks.
+        # "auto" (default) decides per bound graph: sliced while this rank's 32-column panel of the operand (N x 128 B)
+        # stays L2-resident, the all-gather + row-block product otherwise (measured at N = 2M, Hd = 512 on 8 GPUs:
+        # 149 ms / step gathered vs 194 ms sliced, profiles/r2b_bench_c4_n8_*.json; at N = 500k 6.6 vs 11.1 ms)
+        self.exchange_pref = os.environ.get("GCNB_EXCHANGE", "auto") if self.world > 1 else "none"
+        if self.exchange_pref not in ("auto", "slice", "gather", "none"):
+            raise ValueError("GCNB_EXCHANGE must be 'auto', 'slice' or 'gather'")
+        self.exchange = self.exchange_pref
+        self.peer_ok = False
         self.arena = None
         self._slice_plans = {}
         if self.world > 1 and "GCNB_PEER_TIMEOUT_S" in os.environ:
             self.ctx.set_option("peer_timeout_s", int(os.environ["GCNB_PEER_TIMEOUT_S"]))
-        if self.exchange == "slice":
+        if self.exchange_pref in ("slice", "auto"):
             if self.world > 16:
-                self.exchange = "gather"
+                self.exchange_pref = self.exchange = "gather"
             else:
                 try:  # probe once: a tiny arena, mapped by every peer, one device barrier
                     probe = PeerArena(self, 1 << 16)
@@ -499,10 +514,11 @@ class Engine:
                     torch.distributed.barrier(group=self.group)
                     probe.close()
                     torch.distributed.barrier(group=self.group)
+                    self.peer_ok = True
                 except PeerUnavailable as e:
                     import logging
                     logging.warning("NVLink peer memory unavailable (%s): using the all-gather exchange", e)
-                    self.exchange = "gather"
+                    self.exchange_pref = self.exchange = "gather"
         if "GCNB_SPMM_PANEL" in os.environ:  # column-panel width of the panel engine (16 / 32 / 64 floats)
             self.ctx.set_option("spmm_panel", int(os.environ["GCNB_SPMM_PANEL"]))
         if self.world > 1 and "GCNB_SM_MARGIN" in os.environ:
@@ -647,6 +663,8 @@ class Engine:
             self.ctx.sync()
             self.copy_ctx.sync()
             self._uploads = {}
+            if self.exchange_pref == "auto":
+                self.exchange = "slice" if self.peer_ok and X.shape[0] * 128 <= self.SLICE_PANEL_BYTES_MAX else "gather"
             hg = HostGraph(X, A, self.world, self.rank, self.spmm_chunk, need_backward, assume_symmetric,
                            self.hot_density, self.hot_max, self.xt_blocks, allreduce=self._allreduce_host,
                            full_graph=self.exchange == "slice")
@@ -666,6 +684,7 @@ class Engine:
                 self.hot_csr = (torch.empty(hg.hot_ptr.size, dtype=torch.int32, device=self.dev),
                                 torch.empty(max(hg.hot_col.size, 1), dtype=torch.int32, device=self.dev),
                                 torch.empty(max(hg.hot_val.size, 1), dtype=torch.float32, device=self.dev))
+                self.hot_col16 = torch.empty(hg.hot_col.size + 8, dtype=torch.int16, device=self.dev)
                 self._upload_hot(hg)
             self._alloc_buffers(need_backward)
             self._bound_key = key
@@ -708,7 +727,10 @@ class Engine:
         ctx = self.ctx if ctx is None else ctx
         # the hot block travels as CSR (hot-local column ids) and is expanded to the dense N x Kh operand on the device
         for dst, src in zip(self.hot_csr, (hg.hot_ptr, hg.hot_col, hg.hot_val)):
-            if src.size:
+            if src is hg.hot_col and src.size:  # uint16 over PCIe, widened on the device
+                ctx.call("gcnb_h2d", _ptr(self.hot_col16), C.c_void_p(src.ctypes.data), src.nbytes)
+                ctx.call("gcnb_expand_u16_i32", _ptr(self.hot_col16), src.size, _ptr(dst))
+            elif src.size:
                 ctx.call("gcnb_h2d", _ptr(dst), C.c_void_p(src.ctypes.data), src.nbytes)
         ctx.call("gcnb_csr_to_dense_f32", _ptr(self.hot_csr[0]), _ptr(self.hot_csr[1]), _ptr(self.hot_csr[2]),
                  hg.n_loc, hg.kh, _ptr(self.X_hot), hg.kh)
@@ -731,6 +753,8 @@ class Engine:
             self._alloc_buffers_impl(need_backward)
             self._measuring = False
             self.arena = PeerArena(self, self._measured + (1 << 20))
+        else:
+            self._release_arena()
         self._alloc_buffers_impl(need_backward)
 
     def _slice_plan(self, K):

@@ -98,6 +98,10 @@ int gcnb_memset(gcnb_ctx* ctx, void* dst_dev, int byte, size_t bytes);
 int gcnb_copy2d_f32(gcnb_ctx* ctx, const float* src, int32_t ld_src, float* dst, int32_t ld_dst, int32_t rows,
                     int32_t cols);
 
+/* dst[i] = src[i] widened to int32 (device arrays, 16-byte aligned).  Column ids of a matrix with at most 65536 columns
+ * (the BoW features: 10k-50k terms) cross PCIe as uint16 -- a quarter of the CSR bytes less -- and are widened here. */
+int gcnb_expand_u16_i32(gcnb_ctx* ctx, const uint16_t* src, int64_t n, int32_t* dst);
+
 /* ---------------------------------------------------------------- CSR ----------------- */
 /* A CSR matrix resident in device memory plus its work decomposition ("plan"): every row is
  * cut into items of at most `chunk` nonzeros; a row that needs more than one item is a "long"
