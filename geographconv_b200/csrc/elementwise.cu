@@ -270,12 +270,21 @@ __global__ void __launch_bounds__(kThreads) xent_metrics_stage1_kernel(const flo
   }
 }
 __global__ void xent_metrics_stage2_kernel(int nblocks, const float* partial, float* metrics) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  // double accumulation of the per-block sums keeps the reported mean stable for 10^5..10^6 rows
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  // double accumulation of the per-block sums keeps the reported mean stable for 10^5..10^6 rows; one warp, lane l
+  // adds blocks l, l+32, ..., then a fixed-order shuffle tree: deterministic, and 30x shorter than one thread walking
+  // all blocks (60 us, visible at 6 ms per step on 8 GPUs)
   double l = 0.0, c = 0.0;
-  for (int b = 0; b < nblocks; ++b) { l += partial[2 * b]; c += partial[2 * b + 1]; }
-  metrics[0] += (float)l;
-  metrics[1] += (float)c;
+  for (int b = threadIdx.x; b < nblocks; b += 32) { l += partial[2 * b]; c += partial[2 * b + 1]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    l += __shfl_down_sync(0xffffffffu, l, o);
+    c += __shfl_down_sync(0xffffffffu, c, o);
+  }
+  if (threadIdx.x == 0) {
+    metrics[0] += (float)l;
+    metrics[1] += (float)c;
+  }
 }
 
 __global__ void __launch_bounds__(kThreads) xent_grad_kernel(const float* P, int ldp, int C, const int* idx,

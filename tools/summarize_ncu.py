@@ -3,11 +3,11 @@
 
     python tools/summarize_ncu.py launches gpurun_out/launches_r1.csv  > profiles/r1_launches.md
     python tools/summarize_ncu.py full     gpurun_out/prof_r1_raw.csv  > profiles/r1_ncu_full.md
-    python tools/summarize_ncu.py traffic  profiles/r2_ncu_full_raw.csv C3 spmm_panel_kernel 0 - 2,4,14,19 > profiles/roofline_traffic.json
+    python tools/summarize_ncu.py traffic  profiles/r2c_ncu_full_raw.csv C3 spmm_panel_kernel 3+4,6+7,18+19,24+25 > profiles/roofline_traffic.json
 
 ``traffic`` regenerates the file bench.py reads ``roofline.traffic`` from: DRAM bytes per launch (dram__bytes_read.sum +
-dram__bytes_write.sum) and the L2 hit rate of the dominant kernel, averaged over the launches of that kernel whose grid
-has at least the given number of CTAs in x (the full-width A_hat.H products; narrower launches are other products).
+dram__bytes_write.sum) and the L2 hit rate of the dominant kernel, per A_hat.H product at the hidden width (a product is
+two launches of the panel kernel: the 32-column panels and the remainder columns).
 """
 import collections
 import csv
@@ -77,36 +77,41 @@ def _num(v):
     return float(v.replace(",", ""))
 
 
-def traffic(path, workload, kernel, min_grid_x="0", grid_y=None, ids=None):
-    """ids: comma-separated launch numbers (rows of the CSV, 0-based) when the grid alone does not single out the product"""
+def traffic(path, workload, kernel, groups):
+    """groups: comma-separated products, each the launch numbers (rows of the CSV, 0-based) that make up ONE product joined
+    with '+', e.g. 3+4,6+7,18+19,24+25 (the 32-column panels and the remainder-column launch of each A_hat.H product).
+    DRAM bytes are summed inside a product and averaged over the products; the L2 hit rate is weighted by duration."""
     import json
     rows = list(csv.reader(open(path)))
     h, units = rows[0], rows[1]
     col = {name: h.index(name) for name in ("Kernel Name", "Grid Size", "dram__bytes_read.sum", "dram__bytes_write.sum",
                                             "lts__t_sector_hit_rate.pct", "gpu__time_duration.sum")}
     scale = lambda i: {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[i], 1.0)
-    picked = []
-    for n, r in enumerate(rows[2:]):
-        if kernel not in r[col["Kernel Name"]]:
-            continue
-        grid = [int(x) for x in r[col["Grid Size"]].replace("(", "").replace(")", "").split(",")]
-        if grid[0] < int(min_grid_x) or (grid_y not in (None, "-") and grid[1] != int(grid_y)):
-            continue
-        if ids and n not in [int(x) for x in ids.split(",")]:
-            continue
-        rd = _num(r[col["dram__bytes_read.sum"]]) * scale(col["dram__bytes_read.sum"])
-        wr = _num(r[col["dram__bytes_write.sum"]]) * scale(col["dram__bytes_write.sum"])
-        picked.append((n, r[col["Kernel Name"]].split("(")[0], grid, rd, wr, _num(r[col["lts__t_sector_hit_rate.pct"]])))
-    if not picked:
-        raise SystemExit("no launch of %s with grid.x >= %s in %s" % (kernel, min_grid_x, path))
-    rd = sum(p[3] for p in picked) / len(picked)
-    wr = sum(p[4] for p in picked) / len(picked)
-    out = {"workload": workload, "kernel": picked[0][1].replace("void ", "").replace("(anonymous namespace)::", ""),
-           "dram_bytes_per_launch": int(rd + wr), "dram_bytes_read": int(rd), "dram_bytes_write": int(wr),
-           "l2_hit_pct": round(sum(p[5] for p in picked) / len(picked), 2),
-           "launches": [p[0] for p in picked], "grid": picked[0][2],
-           "source": "%s launches %s: dram__bytes_read.sum + dram__bytes_write.sum, mean over %d launches" % (
-               path, "/".join("#%d" % p[0] for p in picked), len(picked))}
+    data = rows[2:]
+    prods = []
+    names = []
+    for g in groups.split(","):
+        rd = wr = dur = hit = 0.0
+        for n in (int(x) for x in g.split("+")):
+            r = data[n]
+            if kernel not in r[col["Kernel Name"]]:
+                raise SystemExit("launch %d is %s, not %s" % (n, r[col["Kernel Name"]][:60], kernel))
+            names.append(r[col["Kernel Name"]].split("(")[0].replace("void ", "").replace("<unnamed>::", "") + " grid " +
+                         r[col["Grid Size"]])
+            t = _num(r[col["gpu__time_duration.sum"]])
+            rd += _num(r[col["dram__bytes_read.sum"]]) * scale(col["dram__bytes_read.sum"])
+            wr += _num(r[col["dram__bytes_write.sum"]]) * scale(col["dram__bytes_write.sum"])
+            hit += _num(r[col["lts__t_sector_hit_rate.pct"]]) * t
+            dur += t
+        prods.append((rd, wr, hit / dur, dur))
+    k = len(prods)
+    out = {"workload": workload, "kernel": kernel,
+           "dram_bytes_per_launch": int(sum(p[0] + p[1] for p in prods) / k),
+           "dram_bytes_read": int(sum(p[0] for p in prods) / k), "dram_bytes_write": int(sum(p[1] for p in prods) / k),
+           "l2_hit_pct": round(sum(p[2] for p in prods) / k, 2),
+           "launches_of_one_product": sorted(set(names)),
+           "source": "%s, products %s: dram__bytes_read.sum + dram__bytes_write.sum summed inside a product (all its "
+                     "launches), mean over %d products" % (path, groups, k)}
     print(json.dumps(out, indent=1))
 
 
