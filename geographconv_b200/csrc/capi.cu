@@ -101,6 +101,7 @@ static int* option_slot(gcnb_ctx* ctx, const char* name) {
   if (!strcmp(name, "gemm_tc")) return &ctx->gemm_tc;
   if (!strcmp(name, "sm_margin")) return &ctx->sm_margin;
   if (!strcmp(name, "spmm_panel")) return &ctx->spmm_panel;
+  if (!strcmp(name, "spmm_sliced_engine")) return &ctx->spmm_sliced_engine;
   if (!strcmp(name, "spmm_panel_policy")) return &ctx->spmm_panel_policy;
   if (!strcmp(name, "peer_timeout_s")) return &ctx->peer_timeout_s;
   if (!strcmp(name, "prof_mask")) return reinterpret_cast<int*>(&ctx->prof_mask);

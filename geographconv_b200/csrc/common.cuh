@@ -44,6 +44,7 @@ struct gcnb_ctx {
   int spmm_unroll = 0;  // 0 = auto
   int sm_margin = 0;    // SMs the persistent SpMM kernel leaves free (for concurrently running NCCL kernels)
   int spmm_panel = 32;  // column-panel width (floats: 16, 32, 64) of the L2-resident panel engine (engine 2)
+  int spmm_sliced_engine = -1;  // gather engine of the feature-sliced product: -1 by operand size, else 0 / 1 / 2
   int spmm_panel_policy = 1;  // gathers of the panel engine: 0 default policy, 1 L2 evict_last hint, 2 + L1 allocation
   int gemm_tc = 1;       // tcgen05 GEMMs where supported (0 = CUDA-core fp32 kernels only)
   int tc_launches = 0;

@@ -978,9 +978,30 @@ extern "C" int gcnb_spmm_csr_sliced_f32(gcnb_ctx* ctx, const gcnb_csr* A, const 
   if (epi) {
     p.bias = epi->bias; p.act = epi->act;
   }
-  // panel width: the context's "spmm_panel" option (32 unless set: 64 gathers 256-byte rows, for operands whose
-  // 128-byte panel no longer fits L2)
-  return launch_panels(ctx, p, A->n_rows, width, ctx->spmm_unroll, false);
+  // Gather engine of the slice ("spmm_sliced_engine": -1 = by size).  While this rank's 32-column panel of the operand
+  // (n_cols x 128 B) fits L2 the panel engine keeps the gathers on chip; beyond that (N = 2M: 256 MB) every gather is
+  // an HBM access anyway and the bulk-copy engine moves whole slice rows (width x 4 bytes) with one cp.async.bulk each.
+  int engine = ctx->spmm_sliced_engine;
+  if (engine != 0 && engine != 1 && engine != 2) engine = (size_t)A->n_cols * 128 > ((size_t)80 << 20) ? 1 : 2;
+  if (engine == 2) return launch_panels(ctx, p, A->n_rows, width, ctx->spmm_unroll, false);  // width: "spmm_panel"
+  if (engine == 1 && (!ctx->ws || ctx->ws_bytes < 256))
+    return gcnb_fail(ctx, GCNB_E_WORKSPACE, "spmm needs %s%lld workspace bytes, have %lld", "", 256LL, (long long)ctx->ws_bytes);
+  for (int c0 = 0; c0 < width; c0 += kMaxPassCols) {
+    const int w = (width - c0) < kMaxPassCols ? (width - c0) : kMaxPassCols;
+    p.col0 = c0;
+    p.pcol0 = 0;
+    p.nf4 = w / 4;
+    p.ldp = w;
+    int rc;
+    switch ((p.nf4 + 31) / 32) {
+      case 1: rc = launch_pass<1>(ctx, p, engine, 2); break;
+      case 2: rc = launch_pass<2>(ctx, p, engine, 2); break;
+      case 3: rc = launch_pass<3>(ctx, p, engine, 2); break;
+      default: rc = launch_pass<4>(ctx, p, engine, 2); break;
+    }
+    if (rc != GCNB_OK) return rc;
+  }
+  return GCNB_OK;
 }
 
 extern "C" int gcnb_row_softmax_f32(gcnb_ctx* ctx, float* C, int32_t ldc, int32_t n_rows, int32_t K, float* logits) {

@@ -519,6 +519,8 @@ class Engine:
                     import logging
                     logging.warning("NVLink peer memory unavailable (%s): using the all-gather exchange", e)
                     self.exchange_pref = self.exchange = "gather"
+        if "GCNB_SLICED_ENGINE" in os.environ:  # gather engine of the feature-sliced product (default: by size)
+            self.ctx.set_option("spmm_sliced_engine", int(os.environ["GCNB_SLICED_ENGINE"]))
         if "GCNB_SPMM_PANEL" in os.environ:  # column-panel width of the panel engine (16 / 32 / 64 floats)
             self.ctx.set_option("spmm_panel", int(os.environ["GCNB_SPMM_PANEL"]))
         if self.world > 1 and "GCNB_SM_MARGIN" in os.environ:
@@ -800,9 +802,12 @@ class Engine:
             self.dT = self._zeros(n, maxld)
         # workspace: the largest scratch any op of the step needs
         need = 1 << 20
+        ka = max(widths + [L.output_size])
+        if self.exchange == "slice":  # a rank multiplies its column slice only
+            ka = max(int(self._slice_plan(w)[1][self.rank]) for w in set(widths + [L.output_size]))
         for a in (self.A, self.AT):
             if a is not None:
-                need = max(need, self.lib.gcnb_spmm_workspace_bytes(C.byref(a.struct), max(widths + [L.output_size])))
+                need = max(need, self.lib.gcnb_spmm_workspace_bytes(C.byref(a.struct), max(ka, 4)))
         need = max(need, self.lib.gcnb_spmm_workspace_bytes(C.byref(self.X.struct), hd))
         need = max(need, self.lib.gcnb_highway_workspace_bytes(0, max(widths)))
         wall = max(widths + [L.output_size, hd])

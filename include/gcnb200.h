@@ -75,7 +75,8 @@ int gcnb_set_workspace(gcnb_ctx* ctx, void* dev_ptr, size_t bytes);
  * default cache policy, 1 = L2 evict_last hint (default), 2 = evict_last with L1 allocation),
  * "spmm_unroll" (nonzeros gathered per batch), "gemm_tc" (1 = tcgen05 path where supported, the
  * default), "tc_launches" (read-only count of tcgen05 kernels launched), "sm_margin" (SMs the persistent
- * SpMM kernel leaves to concurrently running collectives), "prof_mask" (bit t set: ops of gcnb_tag t are timed while
+ * SpMM kernel leaves to concurrently running collectives), "spmm_sliced_engine" (gather engine of gcnb_spmm_csr_sliced_f32: -1 = by
+ * operand size, the default; 0 / 1 / 2 as above), "prof_mask" (bit t set: ops of gcnb_tag t are timed while
  * profiling is on; default all), "peer_timeout_s" (gcnb_peer_barrier). */
 int gcnb_set_option(gcnb_ctx* ctx, const char* name, int value);
 int gcnb_get_option(const gcnb_ctx* ctx, const char* name, int* value);
