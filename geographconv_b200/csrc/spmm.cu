@@ -978,12 +978,21 @@ extern "C" int gcnb_spmm_csr_sliced_f32(gcnb_ctx* ctx, const gcnb_csr* A, const 
   if (epi) {
     p.bias = epi->bias; p.act = epi->act;
   }
-  // Gather engine of the slice ("spmm_sliced_engine": -1 = by size).  While this rank's 32-column panel of the operand
-  // (n_cols x 128 B) fits L2 the panel engine keeps the gathers on chip; beyond that (N = 2M: 256 MB) every gather is
-  // an HBM access anyway and the bulk-copy engine moves whole slice rows (width x 4 bytes) with one cp.async.bulk each.
+  // Gather engine of the slice: the panel engine unless "spmm_sliced_engine" names another (0 / 1; both verified
+  // bit-identical).  Measured at N = 2M, degree 64, slices of 64 columns on 8 GPUs (profiles/r2b_bench_c4_n8_*.json,
+  // r2d_bench_c4_n8_slice_bulk.json): 32-column panels 27.2 ms per product (the 256 MB panel thrashes L2), 64-column
+  // panels 13.7 ms, bulk-copy engine with 256-byte rows 15.6 ms -- against 4.7 ms + 6.6 ms of all-gather for the
+  // row-block product, which is why the engine picks the all-gather exchange for graphs that large.
   int engine = ctx->spmm_sliced_engine;
-  if (engine != 0 && engine != 1 && engine != 2) engine = (size_t)A->n_cols * 128 > ((size_t)80 << 20) ? 1 : 2;
-  if (engine == 2) return launch_panels(ctx, p, A->n_rows, width, ctx->spmm_unroll, false);  // width: "spmm_panel"
+  if (engine != 0 && engine != 1) engine = 2;
+  if (engine == 2) {
+    const bool big = (size_t)A->n_cols * 128 > ((size_t)80 << 20) && width >= 64 && ctx->spmm_panel == 32;
+    const int saved = ctx->spmm_panel;
+    if (big) ctx->spmm_panel = 64;  // panel no longer L2-resident: gather 256-byte rows
+    const int rc = launch_panels(ctx, p, A->n_rows, width, ctx->spmm_unroll, false);
+    ctx->spmm_panel = saved;
+    return rc;
+  }
   if (engine == 1 && (!ctx->ws || ctx->ws_bytes < 256))
     return gcnb_fail(ctx, GCNB_E_WORKSPACE, "spmm needs %s%lld workspace bytes, have %lld", "", 256LL, (long long)ctx->ws_bytes);
   for (int c0 = 0; c0 < width; c0 += kMaxPassCols) {

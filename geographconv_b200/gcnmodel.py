@@ -367,13 +367,20 @@ class SparseConvolutionDenseLayer2(SparseConvolutionDenseLayer):
 
 
 class ConvolutionDenseLayer2(_SingleLayer):
-    """act(A.(x.W) + b) for dense x (gcnmodel.py:114-136)."""
+    """act((A.(x.W) + b)[target_indices, :]) for dense x (gcnmodel.py:114-136).  The row gather only happens when the
+    layer was built with ``use_target_indices=True`` AND ``target_indices`` is passed (gcnmodel.py:121-123,134-135); the
+    activations are element-wise or row-wise, so gathering the rows of the activated matrix is the same thing."""
 
-    def get_output_for(self, input, A=None, **kwargs):
+    def __init__(self, num_units, nonlinearity='tanh', device=None, use_target_indices=False):
+        super().__init__(num_units, nonlinearity, device)
+        self.use_target_indices = use_target_indices
+
+    def get_output_for(self, input, A=None, target_indices=None, **kwargs):
         from .layers import graph_conv_dense
         self._init(np.shape(input)[1])
-        return graph_conv_dense(A, np.asarray(input, dtype=np.float32), self.W, self.b, self.nonlinearity,
-                                device=self._device)
+        out = graph_conv_dense(A, np.asarray(input, dtype=np.float32), self.W, self.b, self.nonlinearity,
+                               device=self._device)
+        return _take_rows(out, target_indices, self.use_target_indices)
 
 
 class ConvolutionDenseLayer3(ConvolutionDenseLayer2):
@@ -381,6 +388,9 @@ class ConvolutionDenseLayer3(ConvolutionDenseLayer2):
 
     def __init__(self, num_units, nonlinearity='softmax', device=None):
         super().__init__(num_units, nonlinearity, device)
+
+    def get_output_for(self, input, A=None, **kwargs):  # no target_indices in the reference's signature (gcnmodel.py:148)
+        return super().get_output_for(input, A=A)
 
 
 class ConvolutionDenseLayer_zero(ConvolutionDenseLayer2):

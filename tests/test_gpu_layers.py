@@ -40,6 +40,20 @@ def test_convolution_variants(data):
     lay = m.DenseLayer2(32, 'sigmoid', use_target_indices=True)
     out = lay.get_output_for(x, target_indices=ti)
     _close(out, gcn_ref.sigmoid(x @ lay.W + lay.b[None, :])[ti])
+    # ConvolutionDenseLayer2: the gather needs use_target_indices AND target_indices (gcnmodel.py:121-123,134-135)
+    lay = m.ConvolutionDenseLayer2(40, 'tanh', use_target_indices=True)
+    lay._init(x.shape[1])
+    want = np.tanh(A @ (x @ lay.W) + lay.b[None, :])
+    _close(lay.get_output_for(x, A=A, target_indices=ti), want[ti])
+    _close(lay.get_output_for(x, A=A), want)
+    lay2 = m.ConvolutionDenseLayer2(40, 'tanh')
+    lay2._init(x.shape[1])
+    _close(lay2.get_output_for(x, A=A, target_indices=ti), np.tanh(A @ (x @ lay2.W) + lay2.b[None, :]))
+    # ConvolutionDenseLayer3 without a graph: softmax(x.W + b) (gcnmodel.py:152-157)
+    lay3 = m.ConvolutionDenseLayer3(9)
+    lay3._init(x.shape[1])
+    _close(lay3.get_output_for(x), gcn_ref.softmax_rows(x @ lay3.W + lay3.b[None, :]))
+    _close(lay3.get_output_for(x, A=A), gcn_ref.softmax_rows(A @ (x @ lay3.W) + lay3.b[None, :]))
 
 
 def test_sparse_input_variants(data):
