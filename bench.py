@@ -249,6 +249,7 @@ def run_gpu(args, cfg, wname):
         eng.ctx.set_option("spmm_variant", args.spmm_variant)
     if args.gemm_tc is not None:
         eng.ctx.set_option("gemm_tc", args.gemm_tc)
+        eng.side_ctx.set_option("gemm_tc", args.gemm_tc)
     y_tr, y_dev = Y[tr], Y[dev]
     t_bind = time.time()
     eng.bind(X, A, need_backward=True, assume_symmetric=True)  # symmetric by construction (synth.synthetic_graph)
@@ -286,10 +287,10 @@ def run_gpu(args, cfg, wname):
     # inside the timed region only the dominant kernel (the A_hat.H product at the hidden width) carries CUDA events;
     # the full per-op split comes from an instrumented pass of the same steps afterwards (two event records around every
     # one of the ~80 ops of a step are measurable at 7 ms per step)
-    eng.ctx.set_option("prof_mask", 1 << capi_tag("spmm_a"))
-    eng.ctx.prof_enable(True)
-    eng.ctx.prof_reset()
-    launches0 = eng.ctx.launch_count()
+    eng.prof_mask(1 << capi_tag("spmm_a"))
+    eng.prof_enable(True)
+    eng.prof_reset()
+    launches0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_host0 = time.perf_counter()
@@ -301,8 +302,8 @@ def run_gpu(args, cfg, wname):
     barrier()
     clocks = sampler.stop() if sampler else None
     ms = e0.elapsed_time(e1)
-    launches = eng.ctx.launch_count() - launches0
-    prof = eng.ctx.prof_collect()
+    launches = eng.launch_count() - launches0
+    prof = eng.prof_collect()
     metrics = eng.read_metrics()
     tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -356,16 +357,16 @@ def run_gpu(args, cfg, wname):
 
     # ---- instrumented pass: per-op split (every tag timed), NCCL collectives timed with their own events ----
     split_steps = max(1, min(args.steps, 5))
-    eng.ctx.set_option("prof_mask", -1)
-    eng.ctx.prof_reset()
+    eng.prof_mask(-1)
+    eng.prof_reset()
     eng.time_nccl = True
     eng.nccl_ms()
     barrier()
     for i in range(split_steps):
         step_resident(args.warmup + args.steps + i)
     barrier()
-    prof_all = eng.ctx.prof_collect()
-    eng.ctx.prof_enable(False)
+    prof_all = eng.prof_collect()
+    eng.prof_enable(False)
     split = {k: round(v[0] / split_steps, 4) for k, v in prof_all.items()}
     split["nccl"] = round(eng.nccl_ms() / split_steps, 4)
     eng.time_nccl = False
@@ -416,7 +417,9 @@ def run_gpu(args, cfg, wname):
                 "roofline": roof, "split_ms_per_step": split,
                 "split_note": "per-op CUDA events from an instrumented pass of %d further steps (rank 0); `sync` = peer "
                               "barriers incl. waiting for the slowest rank, `comm` = slice pushes not fused into a producer, "
-                              "`nccl` = all-gather / all-reduce collectives" % split_steps,
+                              "`nccl` = all-gather / all-reduce collectives.  Weight-gradient GEMMs run on a second stream "
+                              "next to the SpMM / element-wise kernels (side_stream: %s), so the entries overlap in time and "
+                              "may sum to more than ms_per_step" % (split_steps, eng.use_side),
                 "host_issue_ms_per_step": t_issue / args.steps * 1e3,
                 "peak_device_bytes_per_rank": int(mem_peak.item()),
                 "exchange_bytes_per_product": eng.conv_exchange_bytes(hd),

@@ -489,6 +489,19 @@ class Engine:
         # exposed; the forward pass runs under the copies of A_hat and X^T (see bind / _wait_upload)
         self.copy_stream = torch.cuda.Stream(self.dev)
         self.copy_ctx = capi.Context(int(device), C.c_void_p(self.copy_stream.cuda_stream))
+        # Weight-gradient products (x^T.V: a reduction over the nodes on the tensor cores) feed nothing but the optimiser,
+        # so they CAN leave the critical chain of the backward pass: GCNB_SIDE_STREAM=1 runs them on a second,
+        # higher-priority stream with a context (= workspace) of their own, next to the L2- / HBM-bound SpMM and
+        # element-wise kernels of the main stream.  Measured on C3, one B200 (profiles/r2e_bench_c3_side{0,1}.json): 40.1 ms
+        # per step with the side stream against 37.5 ms in line -- the co-resident tcgen05 CTAs take registers and L2
+        # bandwidth from the latency-bound panel SpMM (A_hat products 2.25 -> 2.87 ms, X^T.dz 4.9 -> 8.2 ms) and cost more
+        # than the 3.9 ms of GEMM they hide.  Off by default; kept because the trade flips if the SpMM stops being
+        # L2-bound.
+        self.use_side = os.environ.get("GCNB_SIDE_STREAM", "0") == "1"
+        self.side_stream = torch.cuda.Stream(self.dev, priority=-1)
+        self.side_ctx = capi.Context(int(device), C.c_void_p(self.side_stream.cuda_stream))
+        self.side_ws = None
+        self._side_readers = {}   # data_ptr of a buffer -> event after which the side stream no longer reads it
         self._uploads = {}
         # exchange design of the graph convolutions (module docstring); "slice" needs CUDA IPC between the ranks.
         # "auto" (default) decides per bound graph: sliced while this rank's 32-column panel of the operand (N x 128 B)
@@ -797,7 +810,8 @@ class Engine:
         if need_backward:
             self.G = self._zeros(n, self.ldc)
             self.U = self._zeros(n, maxld)
-            self.dX = self._zeros(n, maxld)
+            self.U2 = self._zeros(n, maxld)  # V = A^T.dHpre alternates between U2 and U: the weight-gradient product of
+            self.dX = self._zeros(n, maxld)  # one layer (side stream) may still read its V while the next V is written
             self.dH = self._zeros(n, maxld)
             self.dT = self._zeros(n, maxld)
         # workspace: the largest scratch any op of the step needs
@@ -826,6 +840,17 @@ class Engine:
             need = max(need, self.lib.gcnb_gemm_workspace_bytes(1, wmax, wmax, max(n, 1)))
             need = max(need, 2 * self.lib.gcnb_colsum_workspace_bytes(n, wmax))
         self._ensure_ws(need)
+        if need_backward and self.use_side:
+            wmax = max(widths + [L.output_size])
+            side_need = self.lib.gcnb_gemm_workspace_bytes(1, wmax, wmax, max(n, 1))
+            if self.kh:
+                side_need = max(side_need, self.lib.gcnb_gemm_workspace_bytes(1, self.kh, hd, max(n, 1)))
+            side_need = max(int(side_need), 1 << 20)
+            if self.side_ws is None or self.side_ws.numel() < side_need:
+                self.side_ctx.sync()
+                self.side_ws = torch.empty(side_need, dtype=torch.uint8, device=self.dev)
+                self.side_ctx.call("gcnb_set_workspace", _ptr(self.side_ws), self.side_ws.numel())
+            self.side_stream.wait_stream(torch.cuda.current_stream(self.dev))
         self._fence()
 
     def index_arrays(self, idx, labels=None, force_upload=False):
@@ -895,6 +920,58 @@ class Engine:
         if whole or w <= 0 or w >= ld:
             return [(0, ld, K)]
         return [(c0, min(w, ld - c0), min(K - c0, min(w, ld - c0))) for c0 in range(0, ld, w) if c0 < K]
+
+    # ---- side stream: weight-gradient GEMMs off the critical chain ----
+    def _side_wgrad(self, M, N, K, A, lda, B, ldb, Cg, ldc, reads):
+        """Cg[M x N] = A^T . B (A: K x M, B: K x N; K = rows of this rank) on the side stream, after everything the main
+        stream has enqueued so far.  ``reads``: the device tensors it reads that the main stream will overwrite later
+        (``_before_write`` makes the main stream wait for this product first)."""
+        if K == 0:
+            return
+        if not self.use_side:
+            self._gemm(1, 0, M, N, K, A, lda, B, ldb, Cg, ldc)
+            return
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        self.side_stream.wait_event(ev)
+        p = lambda x: x if isinstance(x, C.c_void_p) or x is None else _ptr(x)
+        self.side_ctx.call("gcnb_gemm_f32", 1, 0, M, N, K, p(A), lda, p(B), ldb, p(Cg), ldc, 0, None, 0)
+        done = torch.cuda.Event()
+        done.record(self.side_stream)
+        for t in reads:
+            self._side_readers[t.data_ptr()] = done
+
+    def _before_write(self, *bufs):
+        """Main stream: wait until the side stream has finished reading these buffers (no-op when it never did)."""
+        for t in bufs:
+            ev = self._side_readers.pop(t.data_ptr(), None)
+            if ev is not None:
+                self.stream.wait_event(ev)
+
+    def _join_side(self):
+        if self.use_side:
+            self.stream.wait_stream(self.side_stream)
+            self._side_readers = {}
+
+    # per-op profiling over both contexts (bench.py)
+    def prof_enable(self, on=True):
+        self.ctx.prof_enable(on)
+        self.side_ctx.prof_enable(on)
+
+    def prof_mask(self, mask):
+        self.ctx.set_option("prof_mask", mask)
+        self.side_ctx.set_option("prof_mask", mask)
+
+    def prof_reset(self):
+        self.ctx.prof_reset()
+        self.side_ctx.prof_reset()
+
+    def prof_collect(self):
+        a, b = self.ctx.prof_collect(), self.side_ctx.prof_collect()
+        return {k: (a[k][0] + b[k][0], a[k][1] + b[k][1]) for k in a}
+
+    def launch_count(self):
+        return self.ctx.launch_count() + self.side_ctx.launch_count()
 
     # CUDA-event timing of the NCCL collectives (bench.py's split; off by default)
     def _nccl_tick(self, stream):
@@ -1109,7 +1186,7 @@ class Engine:
         self._conv_finish(pending, self.A_out if self.AT is None else self.AT_out, U, self.ldc, Cn)
         gW, ldgw = self._gptr("Wout")
         Wout, ldwo = self._pptr("Wout")
-        self._gemm(1, 0, width, Cn, n, x, ldx, U, self.ldc, gW, ldgw)          # dWout = x^T.U
+        self._side_wgrad(width, Cn, n, x, ldx, U, self.ldc, gW, ldgw, reads=(self.U,))   # dWout = x^T.U
         dX = self.dX.view(-1)[: self.nbuf * ldx].view(self.nbuf, ldx)
         self._gemm(0, 1, n, width, Cn, U, self.ldc, Wout, ldwo, dX, ldx)        # dx = U.Wout^T
         for i in reversed(range(len(L.layers))):
@@ -1120,9 +1197,11 @@ class Engine:
             ldin = self.ldh[i]
             n_in, n_out = l["n_in"], l["n_out"]
             ldy = self.ldh[i + 1]
+            Vbuf = self.U2 if (len(L.layers) - 1 - i) % 2 == 0 else self.U
             if l["kind"] == "hw":
                 dH = self.dH.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
                 dT = self.dT.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
+                self._before_write(self.dT)
                 gWh, ldgh = self._gptr("Wh%d" % k)
                 gbh, _ = self._gptr("bh%d" % k)
                 gWt, ldgt = self._gptr("Wt%d" % k)
@@ -1132,16 +1211,17 @@ class Engine:
                 self.ctx.call("gcnb_highway_bwd_bias_f32", n, n_out, ldy, _ptr(dX), _ptr(xin), _ptr(b["H"]),
                               _ptr(b["T"]), self.act, _ptr(dH), _ptr(dT), _ptr(dX), gbh, gbt)
                 pending = self._conv_begin(dH, n_out, pushed=self._push_done(armed))
-                V = self.U.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
+                V = Vbuf.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
                 Wh, ldwh = self._pptr("Wh%d" % k)
                 Wt, ldwt = self._pptr("Wt%d" % k)
-                # everything that does not need V = A^T.dHpre runs while its operand is being exchanged
-                self._gemm(1, 0, n_in, n_out, n, xin, ldin, dT, ldy, gWt, ldgt)     # dWt = x^T.dTpre
+                # dWt = x^T.dTpre needs nothing from the convolution: side stream, under the SpMM
+                self._side_wgrad(n_in, n_out, n, xin, ldin, dT, ldy, gWt, ldgt, reads=(self.dT,))
                 split_dgrad = self.exchange == "gather"  # a GEMM of its own keeps the all-gather of dHpre covered
                 if split_dgrad:
                     self._gemm(0, 1, n, n_in, n_out, dT, ldy, Wt, ldwt, dX, ldin, accumulate=1)  # dx += dTpre.Wt^T
+                self._before_write(Vbuf)
                 self._conv_finish(pending, csrT, V, ldy, n_out)                     # V = A^T.dHpre
-                self._gemm(1, 0, n_in, n_out, n, xin, ldin, V, ldy, gWh, ldgh)      # dWh = x^T.V
+                self._side_wgrad(n_in, n_out, n, xin, ldin, V, ldy, gWh, ldgh, reads=(Vbuf,))   # dWh = x^T.V
                 if split_dgrad:
                     self._gemm(0, 1, n, n_in, n_out, V, ldy, Wh, ldwh, dX, ldin, accumulate=1)   # dx += V.Wh^T
                 elif n > 0:  # one pass over dx: dx += dTpre.Wt^T + V.Wh^T
@@ -1154,11 +1234,12 @@ class Engine:
                 self.ctx.call("gcnb_act_bwd_bias_f32", n, n_out, ldy, _ptr(dX), _ptr(b["Y"]), self.act, 0.0, 0, 0,
                               _ptr(dP), gb)
                 pending = self._conv_begin(dP, n_out, pushed=self._push_done(armed))
-                V = self.U.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
+                V = Vbuf.view(-1)[: self.nbuf * ldy].view(self.nbuf, ldy)
+                self._before_write(Vbuf)
                 self._conv_finish(pending, csrT, V, ldy, n_out)
                 gW, ldgw = self._gptr("W%d" % k)
                 W, ldw = self._pptr("W%d" % k)
-                self._gemm(1, 0, n_in, n_out, n, xin, ldin, V, ldy, gW, ldgw)
+                self._side_wgrad(n_in, n_out, n, xin, ldin, V, ldy, gW, ldgw, reads=(Vbuf,))
                 dXn = self.dX.view(-1)[: self.nbuf * ldin].view(self.nbuf, ldin)
                 self._gemm(0, 1, n, n_in, n_out, V, ldy, W, ldw, dXn, ldin)
                 dX = dXn
@@ -1170,10 +1251,12 @@ class Engine:
         gb0, _ = self._gptr("b0")
         self.ctx.call("gcnb_act_bwd_bias_f32", n, hd, ld0, _ptr(dX), _ptr(self.H0), self.act, p, int(seed) & (2**64 - 1),
                       int(self.r0), _ptr(dX), gb0)
+        if self.kh:  # hot columns: dense wgrad on the tensor cores (side stream), under the cold-column SpMM
+            self._side_wgrad(self.kh, hd, n, self.X_hot, self.kh, dX, ld0, self.W0_hot, self.ldh[0], reads=())
         self._wait_upload("XT")
         self._spmm(self.XT, dX, ld0, gW0, ldg0, hd)                                 # dW0 = X^T.dz (cold columns)
-        if self.kh:                                                                 # hot columns: dense wgrad
-            self._gemm(1, 0, self.kh, hd, n, self.X_hot, self.kh, dX, ld0, self.W0_hot, self.ldh[0])
+        self._join_side()                                                           # every weight gradient is in place
+        if self.kh:
             self.ctx.call("gcnb_scatter_rows_f32", _ptr(self.W0_hot), self.ldh[0], _ptr(self.hot_idx), self.kh, hd,
                           gW0, ldg0)
         if self.world > 1:
