@@ -146,6 +146,9 @@ class Context:
                 "fallback" % (device, rc))
         self.h = h
         self.device = device
+        # tuning knobs every context of the process honours (A/B measurements; defaults are the measured winners)
+        if "GCNB_GEMM_BLO" in os.environ:  # tcgen05 GEMMs: weights' lo tile derived in shared memory (1) or loaded (0)
+            self.set_option("gemm_blo", int(os.environ["GCNB_GEMM_BLO"]))
 
     def close(self):
         if getattr(self, "h", None):

@@ -58,6 +58,8 @@ struct alignas(64) TcParams {
   int ldh;
   float* T;
   int ldt;
+  int blo_in_kernel;  // 1: the converter warps derive the weights' lo tile from the hi tile in shared memory (no B_lo
+                      // TMA load: 36 instead of 56 KB per k-block from L2); 0: B_lo arrives pre-split through mapBlo
   long long* dbg;  // optional per-CTA phase timestamps (tools/gemm_phases.py)
   int dbg_mode;    // tools only: 1 = identity activations, 2 = no stores, 4 = no bias loads
 };
@@ -214,11 +216,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           const long long t0 = dbg ? clock64() : 0;
           mbar_wait(bar_empty + 8 * s, par ^ 1);
           if (dbg) { w_empty += clock64() - t0; dbg[8] = w_empty; }
-          mbar_expect_tx(bar_full + 8 * s, a_bytes + 2 * b_bytes);
+          mbar_expect_tx(bar_full + 8 * s, a_bytes + (p.blo_in_kernel ? 1 : 2) * b_bytes);
           const uint32_t dst = smem_base + s * stage_bytes;
           tma_load_2d(dst, &p.mapA[ph], kb * BK, m0, bar_full + 8 * s);
           tma_load_2d(dst + a_bytes, &p.mapB[ph], kb * BK, n0, bar_full + 8 * s);
-          tma_load_2d(dst + half_bytes + a_bytes, &p.mapBlo[ph], kb * BK, n0, bar_full + 8 * s);
+          if (!p.blo_in_kernel) tma_load_2d(dst + half_bytes + a_bytes, &p.mapBlo[ph], kb * BK, n0, bar_full + 8 * s);
         }
       }
     }
@@ -284,6 +286,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         l.z = v[u].z - __uint_as_float(__float_as_uint(v[u].z) & 0xffffe000u);
         l.w = v[u].w - __uint_as_float(__float_as_uint(v[u].w) & 0xffffe000u);
         *reinterpret_cast<float4*>(lo + 16 * (ct + 256 * u)) = l;
+      }
+      if (p.blo_in_kernel) {  // the weight tile the same way: BN rows x 128 B right behind the activation tile
+        const int nchunks = BN * 8;
+        for (int c = ct; c < nchunks; c += 256) {
+          const float4 w = *reinterpret_cast<const float4*>(hi + a_bytes + 16 * c);
+          float4 l;
+          l.x = w.x - __uint_as_float(__float_as_uint(w.x) & 0xffffe000u);
+          l.y = w.y - __uint_as_float(__float_as_uint(w.y) & 0xffffe000u);
+          l.z = w.z - __uint_as_float(__float_as_uint(w.z) & 0xffffe000u);
+          l.w = w.w - __uint_as_float(__float_as_uint(w.w) & 0xffffe000u);
+          *reinterpret_cast<float4*>(lo + a_bytes + 16 * c) = l;
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor core reads
       __syncwarp();
@@ -718,6 +732,7 @@ int gcnb_gemm_tc(gcnb_ctx* ctx, int transB, int M, int N, int K, const float* A,
   p.kblocks[0] = cdiv(K, BK);
   p.M = M; p.N = N;
   p.C = C; p.ldc = ldc; p.bias = bias; p.act = act; p.accumulate = accumulate;
+  p.blo_in_kernel = ctx->gemm_blo;
   return launch(ctx, p);
 }
 
@@ -756,6 +771,7 @@ int gcnb_gemm_pair_tc(gcnb_ctx* ctx, int transB, int M, int N, int K, const floa
   p.kblocks[0] = p.kblocks[1] = cdiv(K, BK);
   p.M = M; p.N = N;
   p.C = C; p.ldc = ldc; p.bias = nullptr; p.act = GCNB_ACT_LINEAR; p.accumulate = accumulate;
+  p.blo_in_kernel = ctx->gemm_blo;
   return launch(ctx, p);
 }
 
@@ -807,6 +823,7 @@ int gcnb_highway_tc(gcnb_ctx* ctx, int n_rows, int hd, const float* S, int lds, 
   p.bias_t = bt; p.X = X; p.ldx = ldx; p.H = H; p.ldh = ldh; p.T = T; p.ldt = ldt;
   p.dbg = reinterpret_cast<long long*>(ctx->tc_dbg);
   p.dbg_mode = ctx->tc_dbg_mode;
+  p.blo_in_kernel = ctx->gemm_blo;
   return launch(ctx, p);
 }
 

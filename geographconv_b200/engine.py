@@ -810,7 +810,7 @@ class Engine:
         if need_backward:
             self.G = self._zeros(n, self.ldc)
             self.U = self._zeros(n, maxld)
-            self.U2 = self._zeros(n, maxld)  # V = A^T.dHpre alternates between U2 and U: the weight-gradient product of
+            self.U2 = self._zeros(n, maxld) if self.use_side else self.U  # V alternates between U2 and U: the wgrad of
             self.dX = self._zeros(n, maxld)  # one layer (side stream) may still read its V while the next V is written
             self.dH = self._zeros(n, maxld)
             self.dT = self._zeros(n, maxld)
