@@ -37,6 +37,7 @@ Both sum every row in CSR order, so the forward pass is bit-identical to the sin
 """
 from __future__ import annotations
 
+import copy
 import ctypes as C
 import os
 
@@ -136,7 +137,7 @@ def _fingerprint(M):
 class HostCsr:
     """Host-side CSR of one SpMM operand: int32 / fp32 arrays in pinned memory plus the row-item plan."""
 
-    def __init__(self, M, chunk, col_blocks=1):
+    def __init__(self, M, chunk, col_blocks=1, row_groups=1):
         M = M.tocsr()
         if not M.has_sorted_indices:
             M = M.copy()
@@ -155,8 +156,22 @@ class HostCsr:
             # the persistent engine pulls items from a counter, so a short tail pays.  Results do not depend on the
             # order (every item owns its output row or its partial-sum slot).
             lens = items[:, 2] - items[:, 1] if len(items) else np.zeros(0, dtype=np.int32)
-            if len(lens) and int(lens.max()) > int(lens.min()):
+            # Row groups (X only): the items of consecutive row ranges are kept together, longest first inside a group,
+            # so that a product can also be launched group by group while the later rows are still crossing PCIe
+            # (Engine.bind's repeated uploads).  One launch over all items computes the same thing.
+            self.row_bounds = [0, self.shape[0]]
+            self.item_bounds = [0, len(items)]
+            if row_groups > 1 and len(long_rows) == 0 and self.shape[0] >= 64 * row_groups:
+                per = -(-self.shape[0] // int(row_groups))
+                per = -(-per // 128) * 128  # whole 128-row GEMM tiles
+                self.row_bounds = list(range(0, self.shape[0], per)) + [self.shape[0]]
+                gid = items[:, 0] // per
+                items = np.ascontiguousarray(items[np.lexsort((-lens, gid))])
+                self.item_bounds = [0] + list(np.cumsum(np.bincount(gid, minlength=len(self.row_bounds) - 1)))
+            elif len(lens) and int(lens.max()) > int(lens.min()):
                 items = np.ascontiguousarray(items[np.argsort(-lens, kind="stable")])
+        if not hasattr(self, "row_bounds"):
+            self.row_bounds, self.item_bounds = [0, self.shape[0]], [0, len(items)]
         self.col_blocks = int(col_blocks)
         self.rowptr = _pinned(rowptr)
         self.colidx = _pinned(np.ascontiguousarray(M.indices, dtype=np.int32))
@@ -232,7 +247,7 @@ class HostGraph:
     memory across epochs, gcnmain.py:172-179) and cached by the engine."""
 
     def __init__(self, X, A, world, rank, chunk, need_backward, assume_symmetric=None, hot_density=0.0,
-                 hot_max=0, xt_blocks=0, allreduce=None, full_graph=False):
+                 hot_max=0, xt_blocks=0, allreduce=None, full_graph=False, x_groups=1):
         n = X.shape[0]
         self.n = n
         self.n_pad, blocks = row_blocks(n, world)
@@ -265,7 +280,7 @@ class HostGraph:
         self.hot_ptr = _pinned(np.ascontiguousarray(X_hot.indptr, dtype=np.int32)) if self.kh else None
         self.hot_col = _pinned(np.ascontiguousarray(X_hot.indices, dtype=np.uint16)) if self.kh else None  # kh <= 65536
         self.hot_val = _pinned(np.ascontiguousarray(X_hot.data, dtype=np.float32)) if self.kh else None
-        self.X = HostCsr(Xl, chunk)  # the cold columns only when a hot block exists
+        self.X = HostCsr(Xl, chunk, row_groups=x_groups)  # the cold columns only when a hot block exists
         self.A = HostCsr(Al, chunk)
         self.XT = self.AT = None
         self.symmetric = True
@@ -321,6 +336,32 @@ class DeviceCsr:
                 ctx.call("gcnb_expand_u16_i32", _ptr(self.t_col16), host.colidx16.size, _ptr(self.t_colidx))
             elif src.size:
                 ctx.call("gcnb_h2d", _ptr(dst), C.c_void_p(src.ctypes.data), src.nbytes)
+
+    def refill_rows(self, eng, host, a, b, ctx, first):
+        """Copy the nonzeros of rows [a, b) (``first``: and the row pointers and the item plan) to the device."""
+        at = lambda t, off: C.c_void_p(t.data_ptr() + off)
+        if first:
+            for dst, src in ((self.t_rowptr, host.rowptr), (self.t_items, host.items), (self.t_long, host.long_rows)):
+                if src.size:
+                    ctx.call("gcnb_h2d", _ptr(dst), C.c_void_p(src.ctypes.data), src.nbytes)
+        lo, hi = int(host.rowptr[a]), int(host.rowptr[b])
+        if hi <= lo:
+            return
+        if self.t_col16 is not None:
+            ctx.call("gcnb_h2d", at(self.t_col16, 2 * lo), C.c_void_p(host.colidx16.ctypes.data + 2 * lo), 2 * (hi - lo))
+            lo8 = lo & ~7  # the widening kernel wants 16-byte aligned ends; the few ids before lo are already there
+            ctx.call("gcnb_expand_u16_i32", at(self.t_col16, 2 * lo8), hi - lo8, at(self.t_colidx, 4 * lo8))
+        else:
+            ctx.call("gcnb_h2d", at(self.t_colidx, 4 * lo), C.c_void_p(host.colidx.ctypes.data + 4 * lo), 4 * (hi - lo))
+        ctx.call("gcnb_h2d", at(self.t_val, 4 * lo), C.c_void_p(host.val.ctypes.data + 4 * lo), 4 * (hi - lo))
+
+    def group_struct(self, host, g):
+        """The same matrix restricted to the items of row group ``g`` (HostCsr.row_bounds)."""
+        s = GcnbCsr()
+        C.memmove(C.byref(s), C.byref(self.struct), C.sizeof(GcnbCsr))
+        i0, i1 = int(host.item_bounds[g]), int(host.item_bounds[g + 1])
+        s.items, s.n_items = self.t_items.data_ptr() + 16 * i0, i1 - i0
+        return s
 
     def retagged(self, tag):
         """Same device arrays booked under another profiling tag."""
@@ -465,6 +506,9 @@ class Engine:
         # column ranges the rows of X^T are cut into (0 = from the panel working-set rule)
         self.spmm_engine = int(os.environ.get("GCNB_SPMM_ENGINE", "-2"))
         self.xt_blocks = int(os.environ.get("GCNB_XT_BLOCKS", "0"))
+        # repeated uploads (cache_device_inputs = False): X crosses PCIe in this many row groups and the first layer runs
+        # group by group behind the copies (1 = whole matrix first)
+        self.x_groups = max(1, int(os.environ.get("GCNB_X_GROUPS", "8")))
         self.group = group
         self.world = torch.distributed.get_world_size(group) if group is not None else 1
         self.rank = torch.distributed.get_rank(group) if group is not None else 0
@@ -682,7 +726,7 @@ class Engine:
                 self.exchange = "slice" if self.peer_ok and X.shape[0] * 128 <= self.SLICE_PANEL_BYTES_MAX else "gather"
             hg = HostGraph(X, A, self.world, self.rank, self.spmm_chunk, need_backward, assume_symmetric,
                            self.hot_density, self.hot_max, self.xt_blocks, allreduce=self._allreduce_host,
-                           full_graph=self.exchange == "slice")
+                           full_graph=self.exchange == "slice", x_groups=self.x_groups)
             self.host = hg
             self._bound_refs = (X, A)
             self.n, self.n_pad, self.r0, self.r1 = hg.n, hg.n_pad, hg.r0, hg.r1
@@ -709,8 +753,21 @@ class Engine:
             hg = self.host
             # same host objects, fresh copies: on the copy stream, in order of first use, one event per group
             self.copy_stream.wait_stream(self.stream)  # kernels of the previous call are done with the buffers
+            self._x_group_events = []
             for name, pairs in (("X", ((self.X, hg.X),)), ("A", ((self.A, hg.A), (self.AT, hg.AT))),
                                 ("XT", ((self.XT, hg.XT),))):
+                if name == "X" and len(hg.X.row_bounds) > 2:
+                    # X is what the first kernel of the step needs and the largest upload: it travels in row groups,
+                    # one event per group, and forward() runs the first layer group by group behind the copies
+                    rb = hg.X.row_bounds
+                    for g in range(len(rb) - 1):
+                        self.X.refill_rows(self, hg.X, rb[g], rb[g + 1], self.copy_ctx, first=(g == 0))
+                        if hg.kh:
+                            self._upload_hot(hg, self.copy_ctx, rows=(rb[g], rb[g + 1]), first=(g == 0))
+                        ev = torch.cuda.Event()
+                        ev.record(self.copy_stream)
+                        self._x_group_events.append(ev)
+                    continue
                 for d, h in pairs:
                     if d is not None:
                         d.refill(self, h, self.copy_ctx)
@@ -738,8 +795,24 @@ class Engine:
         torch.distributed.all_reduce(t, group=self.group)
         return t.cpu().numpy()
 
-    def _upload_hot(self, hg, ctx=None):
+    def _upload_hot(self, hg, ctx=None, rows=None, first=True):
         ctx = self.ctx if ctx is None else ctx
+        if rows is not None:  # rows [a, b) of the hot block only (``first``: and the row pointers / column list)
+            a, b = rows
+            at = lambda t, off: C.c_void_p(t.data_ptr() + off)
+            if first:
+                ctx.call("gcnb_h2d", _ptr(self.hot_csr[0]), C.c_void_p(hg.hot_ptr.ctypes.data), hg.hot_ptr.nbytes)
+                ctx.call("gcnb_h2d", _ptr(self.hot_idx), C.c_void_p(hg.hot_cols_p.ctypes.data), hg.hot_cols_p.nbytes)
+            lo, hi = int(hg.hot_ptr[a]), int(hg.hot_ptr[b])
+            if hi > lo:
+                ctx.call("gcnb_h2d", at(self.hot_col16, 2 * lo), C.c_void_p(hg.hot_col.ctypes.data + 2 * lo), 2 * (hi - lo))
+                lo8 = lo & ~7
+                ctx.call("gcnb_expand_u16_i32", at(self.hot_col16, 2 * lo8), hi - lo8, at(self.hot_csr[1], 4 * lo8))
+                ctx.call("gcnb_h2d", at(self.hot_csr[2], 4 * lo), C.c_void_p(hg.hot_val.ctypes.data + 4 * lo), 4 * (hi - lo))
+            if b > a:
+                ctx.call("gcnb_csr_to_dense_f32", at(self.hot_csr[0], 4 * a), _ptr(self.hot_csr[1]), _ptr(self.hot_csr[2]),
+                         b - a, hg.kh, at(self.X_hot, 4 * a * hg.kh), hg.kh)
+            return
         # the hot block travels as CSR (hot-local column ids) and is expanded to the dense N x Kh operand on the device
         for dst, src in zip(self.hot_csr, (hg.hot_ptr, hg.hot_col, hg.hot_val)):
             if src is hg.hot_col and src.size:  # uint16 over PCIe, widened on the device
@@ -1117,15 +1190,39 @@ class Engine:
         self._wait_upload("X")
         # SparseInputDenseLayer + dropout: one SpMM with bias/act/dropout fused in the epilogue; when X has a
         # dense hot-column block, X_hot . W0[hot] runs on the tensor cores first and the cold-column SpMM adds to it
-        if self.kh:
-            self.ctx.call("gcnb_gather_rows_f32", W0, ldw0, _ptr(self.hot_idx), self.kh, hd, _ptr(self.W0_hot),
-                          self.ldh[0])
-            self._gemm(0, 0, n, hd, self.kh, self.X_hot, self.kh, self.W0_hot, self.ldh[0], self.H0, self.ldh[0])
         # a highway layer convolves H0 itself (S = A.H0): its column slices leave from this kernel's epilogue
-        armed = self._arm_push(hd) if (L.layers and L.layers[0]["kind"] == "hw") else False
-        self._spmm(self.X, W0, ldw0, self.H0, self.ldh[0], hd, bias=b0, act=self.act, dropout_p=p, seed=seed,
-                   accumulate=2 if self.kh else 0)
-        x_pushed = self._push_done(armed)
+        want_push = bool(L.layers and L.layers[0]["kind"] == "hw")
+        group_events, self._x_group_events = getattr(self, "_x_group_events", []), []
+        if group_events:
+            # X is still crossing PCIe in row groups (bind with force_upload): the first layer follows the copies group
+            # by group -- same kernels, same per-row arithmetic, items of one row group per launch
+            rb = self.host.X.row_bounds
+            x_pushed = want_push
+            for g, ev in enumerate(group_events):
+                self.stream.wait_event(ev)
+                a, b = rb[g], rb[g + 1]
+                at = lambda t, off: C.c_void_p(t.data_ptr() + off)
+                if self.kh:
+                    if g == 0:
+                        self.ctx.call("gcnb_gather_rows_f32", W0, ldw0, _ptr(self.hot_idx), self.kh, hd,
+                                      _ptr(self.W0_hot), self.ldh[0])
+                    self._gemm(0, 0, b - a, hd, self.kh, at(self.X_hot, 4 * a * self.kh), self.kh, self.W0_hot,
+                               self.ldh[0], at(self.H0, 4 * a * self.ldh[0]), self.ldh[0])
+                armed = self._arm_push(hd) if want_push else False
+                part = copy.copy(self.X)
+                part.struct = self.X.group_struct(self.host.X, g)
+                self._spmm(part, W0, ldw0, self.H0, self.ldh[0], hd, bias=b0, act=self.act, dropout_p=p, seed=seed,
+                           accumulate=2 if self.kh else 0)
+                x_pushed = self._push_done(armed) and x_pushed
+        else:
+            if self.kh:
+                self.ctx.call("gcnb_gather_rows_f32", W0, ldw0, _ptr(self.hot_idx), self.kh, hd, _ptr(self.W0_hot),
+                              self.ldh[0])
+                self._gemm(0, 0, n, hd, self.kh, self.X_hot, self.kh, self.W0_hot, self.ldh[0], self.H0, self.ldh[0])
+            armed = self._arm_push(hd) if want_push else False
+            self._spmm(self.X, W0, ldw0, self.H0, self.ldh[0], hd, bias=b0, act=self.act, dropout_p=p, seed=seed,
+                       accumulate=2 if self.kh else 0)
+            x_pushed = self._push_done(armed)
         x, ldx, width = self.H0, self.ldh[0], hd
         self._wait_upload("A")
         for i, l in enumerate(L.layers):

@@ -173,10 +173,22 @@ def test_gemm_simt(tA, tB, M, N, K):
     _close(got, want, atol_scale=3e-6)
 
 
+@pytest.fixture(params=[2, 1], ids=["two_ctas_per_sm", "one_cta_per_sm"])
+def gemm_v(request):
+    """Both tcgen05 GEMM kernels (ctx option gemm_v): the default with two co-resident CTAs per SM and k-blocks of 16
+    floats, and the one-tile-per-SM kernel with k-blocks of 32."""
+    from geographconv_b200 import layers
+    d = layers.get_dev()
+    old = d.ctx.get_option("gemm_v")
+    d.ctx.set_option("gemm_v", request.param)
+    yield request.param
+    d.ctx.set_option("gemm_v", old)
+
+
 @pytest.mark.parametrize("tB", [0, 1])
 @pytest.mark.parametrize("M,N,K", [(257, 300, 300), (1000, 129, 300), (1000, 300, 256), (128, 32, 8), (3000, 512, 300),
-                                   (77, 5, 3), (130, 160, 1000)])
-def test_gemm_tcgen05_3xtf32(tB, M, N, K):
+                                   (77, 5, 3), (130, 160, 1000), (1000, 304, 17), (513, 170, 48), (4000, 256, 1024)])
+def test_gemm_tcgen05_3xtf32(tB, M, N, K, gemm_v):
     """tcgen05 path (3xTF32 split): fp32-grade accuracy against a float64 product."""
     from geographconv_b200 import layers
     rng = np.random.RandomState(M + N + K + tB)
@@ -192,7 +204,7 @@ def test_gemm_tcgen05_3xtf32(tB, M, N, K):
 
 @pytest.mark.parametrize("M,N,K", [(300, 300, 5000), (129, 300, 20000), (300, 256, 777), (40, 24, 100), (512, 512, 4096),
                                    (300, 300, 31), (7, 3, 5), (1536, 300, 3000), (2048, 129, 700)])
-def test_wgrad_tcgen05_split_k(M, N, K):
+def test_wgrad_tcgen05_split_k(M, N, K, gemm_v):
     """dW = x^T . V on tensor cores: MN-major operands, split over the node dimension, deterministic."""
     from geographconv_b200 import layers
     rng = np.random.RandomState(M + N + K)
@@ -209,7 +221,7 @@ def test_wgrad_tcgen05_split_k(M, N, K):
     _close(layers.gemm(A, B, transA=True, accumulate_into=C0, tc=1), C0 + want, atol_scale=3e-6)
 
 
-def test_gemm_tcgen05_bias_act_accumulate():
+def test_gemm_tcgen05_bias_act_accumulate(gemm_v):
     from geographconv_b200 import layers
     rng = np.random.RandomState(12)
     A = (0.1 * rng.randn(700, 300)).astype(np.float32)
@@ -233,8 +245,8 @@ def test_gemm_bias_act_and_accumulate():
 
 
 @pytest.mark.parametrize("tc", [0, 1])
-@pytest.mark.parametrize("n,hd", [(1000, 300), (777, 40), (129, 512)])
-def test_highway_forward(n, hd, tc):
+@pytest.mark.parametrize("n,hd", [(1000, 300), (777, 40), (129, 512), (5000, 129)])
+def test_highway_forward(n, hd, tc, gemm_v):
     from geographconv_b200 import layers
     rng = np.random.RandomState(n)
     S = rng.randn(n, hd).astype(np.float32)
@@ -299,7 +311,7 @@ def test_fused_backward_with_bias_gradients(n, k):
 
 
 @pytest.mark.parametrize("M,N,K,acc", [(1000, 300, 300, 1), (257, 300, 300, 0), (4000, 129, 512, 1)])
-def test_gemm_pair_one_pass(M, N, K, acc):
+def test_gemm_pair_one_pass(M, N, K, acc, gemm_v):
     """gcnb_gemm_pair_f32: C (+)= A1.B1^T + A2.B2^T with both k-loops in one tcgen05 kernel (fp32-grade, 3xTF32)."""
     import ctypes as C
     import torch

@@ -260,3 +260,38 @@ def test_hot_columns_are_chosen_globally():
         np.testing.assert_array_equal(hot_b, hot_all)
         np.testing.assert_array_equal(Xh_b.toarray(), Xh[r0:r1].toarray())
         np.testing.assert_array_equal(Xc_b.toarray(), Xc[r0:r1].toarray())
+
+
+def test_row_grouped_item_plan_covers_every_row_once():
+    """X's row-item plan in row groups (engine.HostCsr(row_groups=...)): every group holds exactly the items of its
+    128-aligned row range, longest first, and the groups together are the ungrouped plan."""
+    from geographconv_b200.engine import HostCsr
+    rng = np.random.RandomState(3)
+    n, f = 5000, 700
+    deg = rng.poisson(12, size=n)
+    deg[::17] = 0
+    indptr = np.zeros(n + 1, dtype=np.int32)
+    np.cumsum(deg, out=indptr[1:])
+    M = sp.csr_matrix((rng.randn(indptr[-1]).astype(np.float32), rng.randint(0, f, size=indptr[-1]).astype(np.int32),
+                       indptr), shape=(n, f))
+    M.sum_duplicates()
+    M.sort_indices()
+    flat = HostCsr(M, 1024)
+    grp = HostCsr(M, 1024, row_groups=8)
+    assert flat.row_bounds == [0, n] and flat.item_bounds == [0, n]
+    rb, ib = grp.row_bounds, grp.item_bounds
+    assert rb[0] == 0 and rb[-1] == n and all(b % 128 == 0 for b in rb[:-1]) and len(rb) == len(ib) and len(rb) > 3
+    items = np.asarray(grp.items).reshape(-1, 4)
+    seen = np.zeros(n, dtype=np.int64)
+    for g in range(len(rb) - 1):
+        part = items[ib[g]:ib[g + 1]]
+        assert ((part[:, 0] >= rb[g]) & (part[:, 0] < rb[g + 1])).all()
+        lens = part[:, 2] - part[:, 1]
+        assert (np.diff(lens) <= 0).all()
+        np.testing.assert_array_equal(part[:, 1], M.indptr[part[:, 0]])
+        np.testing.assert_array_equal(part[:, 2], M.indptr[part[:, 0] + 1])
+        seen[part[:, 0]] += 1
+    assert (seen == 1).all()
+    # a matrix with rows longer than one item keeps the single-group plan (partial sums are per matrix)
+    hub = sp.vstack([M, sp.csr_matrix(np.ones((1, f), dtype=np.float32))]).tocsr()
+    assert HostCsr(hub, 256, row_groups=8).row_bounds == [0, n + 1]
