@@ -102,6 +102,7 @@ static int* option_slot(gcnb_ctx* ctx, const char* name) {
   if (!strcmp(name, "gemm_blo")) return &ctx->gemm_blo;
   if (!strcmp(name, "gemm_v")) return &ctx->gemm_v;
   if (!strcmp(name, "gemm_prefetch")) return &ctx->gemm_prefetch;
+  if (!strcmp(name, "gemm_blo2")) return &ctx->gemm_blo2;
   if (!strcmp(name, "sm_margin")) return &ctx->sm_margin;
   if (!strcmp(name, "spmm_panel")) return &ctx->spmm_panel;
   if (!strcmp(name, "spmm_sliced_engine")) return &ctx->spmm_sliced_engine;

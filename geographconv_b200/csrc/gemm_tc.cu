@@ -547,11 +547,11 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc2_kernel(const __grid_cons
           const long long t0 = dbg ? clock64() : 0;
           mbar_wait(bar_empty + 8 * s, par ^ 1);
           if (dbg) { w_empty += clock64() - t0; dbg[8] = w_empty; }
-          mbar_expect_tx(bar_full + 8 * s, a_bytes + 2 * b_bytes);
+          mbar_expect_tx(bar_full + 8 * s, a_bytes + (p.blo_in_kernel ? 1 : 2) * b_bytes);
           const uint32_t dst = smem_base + s * stage_bytes;
           tma_load_2d(dst, &p.mapA[ph], kb * BK2, m0, bar_full + 8 * s);
           tma_load_2d(dst + a_bytes, &p.mapB[ph], kb * BK2, n0, bar_full + 8 * s);
-          tma_load_2d(dst + half_bytes + a_bytes, &p.mapBlo[ph], kb * BK2, n0, bar_full + 8 * s);
+          if (!p.blo_in_kernel) tma_load_2d(dst + half_bytes + a_bytes, &p.mapBlo[ph], kb * BK2, n0, bar_full + 8 * s);
         }
       }
     }
@@ -565,20 +565,25 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc2_kernel(const __grid_cons
       for (int kb = 0; kb < p.kblocks[ph]; ++kb, ++it) {
         const int s = it % kStages2;
         const uint32_t par = (it / kStages2) & 1;
-        // A_hi.B_lo and A_hi.B_hi need nothing from the converters (the raw tile is the hi operand): they are issued as
-        // soon as the TMA bytes land and run while the converter warps write A_lo; A_lo.B_hi follows
+        // Terms that read raw tiles only (the raw tile is the hi operand) are issued as soon as the TMA bytes land and
+        // run while the converter warps write the residual tiles; the terms with a residual operand follow.
+        // blo_in_kernel: both residuals are made here (A_lo and B_lo), so hi.hi goes first and the two cross terms wait;
+        // otherwise B_lo arrived by TMA and only A_lo.B_hi waits.
         mbar_wait(bar_full + 8 * s, par);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_hi = smem_base + s * stage_bytes, b_hi = a_hi + a_bytes;
         const uint32_t a_lo = a_hi + half_bytes, b_lo = b_hi + half_bytes;
+        const uint32_t first = (kb != 0 || (ph != 0 && !p.hw)) ? 1u : 0u;  // 0: the tile's very first MMA overwrites
         if (lane == 0) {
+          if (!p.blo_in_kernel) {
+#pragma unroll
+            for (int k = 0; k < BK2 / 8; ++k)
+              umma_tf32(tacc, umma_desc_k64(a_hi + 32 * k), umma_desc_k64(b_lo + 32 * k), idesc, k ? 1u : first);
+          }
 #pragma unroll
           for (int k = 0; k < BK2 / 8; ++k)
-            umma_tf32(tacc, umma_desc_k64(a_hi + 32 * k), umma_desc_k64(b_lo + 32 * k), idesc,
-                      (kb | k) != 0 || (ph != 0 && !p.hw));
-#pragma unroll
-          for (int k = 0; k < BK2 / 8; ++k)
-            umma_tf32(tacc, umma_desc_k64(a_hi + 32 * k), umma_desc_k64(b_hi + 32 * k), idesc, 1u);
+            umma_tf32(tacc, umma_desc_k64(a_hi + 32 * k), umma_desc_k64(b_hi + 32 * k), idesc,
+                      (k || !p.blo_in_kernel) ? 1u : first);
         }
         __syncwarp();
         const long long t0 = dbg ? clock64() : 0;
@@ -589,6 +594,11 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc2_kernel(const __grid_cons
 #pragma unroll
           for (int k = 0; k < BK2 / 8; ++k)
             umma_tf32(tacc, umma_desc_k64(a_lo + 32 * k), umma_desc_k64(b_hi + 32 * k), idesc, 1u);
+          if (p.blo_in_kernel) {
+#pragma unroll
+            for (int k = 0; k < BK2 / 8; ++k)
+              umma_tf32(tacc, umma_desc_k64(a_hi + 32 * k), umma_desc_k64(b_lo + 32 * k), idesc, 1u);
+          }
           umma_commit(bar_empty + 8 * s);  // implies tcgen05.fence::before_thread_sync
           if (it == total_kb - 1) umma_commit(bar_acc);
         }
@@ -608,20 +618,27 @@ __global__ void __launch_bounds__(kThreads, 2) gemm_tc2_kernel(const __grid_cons
       if (dbg && ct == 0) { w_full += t1 - t0; dbg[10] = w_full; }
       if (dbg && ct == 0 && it == 0) dbg[2] = clock64();
       // activation tile: 128 rows x 64 B = 512 16-byte chunks, 2 per thread; the raw tile is the hi operand (the tensor
-      // core ignores the low 13 mantissa bits), only lo = a - hi is written, in the same swizzled positions
+      // core ignores the low 13 mantissa bits), only lo = a - hi is written, in the same swizzled positions.
+      // blo_in_kernel: the weight tile right behind it (bn rows x 64 B) the same way -- its residual then never crosses
+      // the L2 -> SM fabric, which is what bounds the main loop (43 B / clk / SM measured in both kernels).
       const unsigned char* hi = smem + (size_t)s * stage_bytes;
       unsigned char* lo = smem + (size_t)s * stage_bytes + half_bytes;
-      float4 v[2];
+      const int n_conv = 512 + (p.blo_in_kernel ? bn * 4 : 0);
+      for (int c0 = 0; c0 < n_conv; c0 += 512) {
+        float4 v[2];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) v[u] = *reinterpret_cast<const float4*>(hi + 16 * (ct + 256 * u));
+        for (int u = 0; u < 2; ++u)
+          v[u] = (c0 + ct + 256 * u < n_conv) ? *reinterpret_cast<const float4*>(hi + 16 * (c0 + ct + 256 * u))
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        float4 l;
-        l.x = v[u].x - __uint_as_float(__float_as_uint(v[u].x) & 0xffffe000u);
-        l.y = v[u].y - __uint_as_float(__float_as_uint(v[u].y) & 0xffffe000u);
-        l.z = v[u].z - __uint_as_float(__float_as_uint(v[u].z) & 0xffffe000u);
-        l.w = v[u].w - __uint_as_float(__float_as_uint(v[u].w) & 0xffffe000u);
-        *reinterpret_cast<float4*>(lo + 16 * (ct + 256 * u)) = l;
+        for (int u = 0; u < 2; ++u) {
+          float4 l;
+          l.x = v[u].x - __uint_as_float(__float_as_uint(v[u].x) & 0xffffe000u);
+          l.y = v[u].y - __uint_as_float(__float_as_uint(v[u].y) & 0xffffe000u);
+          l.z = v[u].z - __uint_as_float(__float_as_uint(v[u].z) & 0xffffe000u);
+          l.w = v[u].w - __uint_as_float(__float_as_uint(v[u].w) & 0xffffe000u);
+          if (c0 + ct + 256 * u < n_conv) *reinterpret_cast<float4*>(lo + 16 * (c0 + ct + 256 * u)) = l;
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor core reads
       __syncwarp();
@@ -1128,7 +1145,7 @@ int gcnb_gemm_tc(gcnb_ctx* ctx, int transB, int M, int N, int K, const float* A,
   p.kblocks[0] = cdiv(K, tl.bk);
   p.M = M; p.N = N;
   p.C = C; p.ldc = ldc; p.bias = bias; p.act = act; p.accumulate = accumulate;
-  p.blo_in_kernel = ctx->gemm_v >= 2 ? 0 : ctx->gemm_blo;
+  p.blo_in_kernel = ctx->gemm_v >= 2 ? ctx->gemm_blo2 : ctx->gemm_blo;
   return launch(ctx, p);
 }
 
@@ -1167,7 +1184,7 @@ int gcnb_gemm_pair_tc(gcnb_ctx* ctx, int transB, int M, int N, int K, const floa
   p.kblocks[0] = p.kblocks[1] = cdiv(K, tl.bk);
   p.M = M; p.N = N;
   p.C = C; p.ldc = ldc; p.bias = nullptr; p.act = GCNB_ACT_LINEAR; p.accumulate = accumulate;
-  p.blo_in_kernel = ctx->gemm_v >= 2 ? 0 : ctx->gemm_blo;
+  p.blo_in_kernel = ctx->gemm_v >= 2 ? ctx->gemm_blo2 : ctx->gemm_blo;
   return launch(ctx, p);
 }
 
@@ -1219,7 +1236,7 @@ int gcnb_highway_tc(gcnb_ctx* ctx, int n_rows, int hd, const float* S, int lds, 
   p.bias_t = bt; p.X = X; p.ldx = ldx; p.H = H; p.ldh = ldh; p.T = T; p.ldt = ldt;
   p.dbg = reinterpret_cast<long long*>(ctx->tc_dbg);
   p.dbg_mode = ctx->tc_dbg_mode;
-  p.blo_in_kernel = ctx->gemm_v >= 2 ? 0 : ctx->gemm_blo;
+  p.blo_in_kernel = ctx->gemm_v >= 2 ? ctx->gemm_blo2 : ctx->gemm_blo;
   return launch(ctx, p);
 }
 

@@ -337,23 +337,26 @@ class DeviceCsr:
             elif src.size:
                 ctx.call("gcnb_h2d", _ptr(dst), C.c_void_p(src.ctypes.data), src.nbytes)
 
-    def refill_rows(self, eng, host, a, b, ctx, first):
-        """Copy the nonzeros of rows [a, b) (``first``: and the row pointers and the item plan) to the device."""
+    def refill_rows(self, eng, host, a, b, ctx, first, phase="both"):
+        """Copy the nonzeros of rows [a, b) (``first``: and the row pointers and the item plan) to the device.
+        ``phase``: "copy" = only the host->device copies, "expand" = only the kernel that widens 16-bit column ids
+        (so that a copy stream carries nothing but copies and never queues behind compute kernels), "both"."""
         at = lambda t, off: C.c_void_p(t.data_ptr() + off)
-        if first:
-            for dst, src in ((self.t_rowptr, host.rowptr), (self.t_items, host.items), (self.t_long, host.long_rows)):
-                if src.size:
-                    ctx.call("gcnb_h2d", _ptr(dst), C.c_void_p(src.ctypes.data), src.nbytes)
         lo, hi = int(host.rowptr[a]), int(host.rowptr[b])
-        if hi <= lo:
-            return
-        if self.t_col16 is not None:
-            ctx.call("gcnb_h2d", at(self.t_col16, 2 * lo), C.c_void_p(host.colidx16.ctypes.data + 2 * lo), 2 * (hi - lo))
+        if phase in ("copy", "both"):
+            if first:
+                for dst, src in ((self.t_rowptr, host.rowptr), (self.t_items, host.items), (self.t_long, host.long_rows)):
+                    if src.size:
+                        ctx.call("gcnb_h2d", _ptr(dst), C.c_void_p(src.ctypes.data), src.nbytes)
+            if hi > lo:
+                if self.t_col16 is not None:
+                    ctx.call("gcnb_h2d", at(self.t_col16, 2 * lo), C.c_void_p(host.colidx16.ctypes.data + 2 * lo), 2 * (hi - lo))
+                else:
+                    ctx.call("gcnb_h2d", at(self.t_colidx, 4 * lo), C.c_void_p(host.colidx.ctypes.data + 4 * lo), 4 * (hi - lo))
+                ctx.call("gcnb_h2d", at(self.t_val, 4 * lo), C.c_void_p(host.val.ctypes.data + 4 * lo), 4 * (hi - lo))
+        if phase in ("expand", "both") and hi > lo and self.t_col16 is not None:
             lo8 = lo & ~7  # the widening kernel wants 16-byte aligned ends; the few ids before lo are already there
             ctx.call("gcnb_expand_u16_i32", at(self.t_col16, 2 * lo8), hi - lo8, at(self.t_colidx, 4 * lo8))
-        else:
-            ctx.call("gcnb_h2d", at(self.t_colidx, 4 * lo), C.c_void_p(host.colidx.ctypes.data + 4 * lo), 4 * (hi - lo))
-        ctx.call("gcnb_h2d", at(self.t_val, 4 * lo), C.c_void_p(host.val.ctypes.data + 4 * lo), 4 * (hi - lo))
 
     def group_struct(self, host, g):
         """The same matrix restricted to the items of row group ``g`` (HostCsr.row_bounds)."""
@@ -761,9 +764,11 @@ class Engine:
                     # one event per group, and forward() runs the first layer group by group behind the copies
                     rb = hg.X.row_bounds
                     for g in range(len(rb) - 1):
-                        self.X.refill_rows(self, hg.X, rb[g], rb[g + 1], self.copy_ctx, first=(g == 0))
+                        # copies only: the kernels that widen the 16-bit ids and expand the hot block run on the engine
+                        # stream in forward(), else they would queue behind the compute kernels and stall the copies
+                        self.X.refill_rows(self, hg.X, rb[g], rb[g + 1], self.copy_ctx, first=(g == 0), phase="copy")
                         if hg.kh:
-                            self._upload_hot(hg, self.copy_ctx, rows=(rb[g], rb[g + 1]), first=(g == 0))
+                            self._upload_hot(hg, self.copy_ctx, rows=(rb[g], rb[g + 1]), first=(g == 0), phase="copy")
                         ev = torch.cuda.Event()
                         ev.record(self.copy_stream)
                         self._x_group_events.append(ev)
@@ -795,23 +800,26 @@ class Engine:
         torch.distributed.all_reduce(t, group=self.group)
         return t.cpu().numpy()
 
-    def _upload_hot(self, hg, ctx=None, rows=None, first=True):
+    def _upload_hot(self, hg, ctx=None, rows=None, first=True, phase="both"):
         ctx = self.ctx if ctx is None else ctx
         if rows is not None:  # rows [a, b) of the hot block only (``first``: and the row pointers / column list)
             a, b = rows
             at = lambda t, off: C.c_void_p(t.data_ptr() + off)
-            if first:
-                ctx.call("gcnb_h2d", _ptr(self.hot_csr[0]), C.c_void_p(hg.hot_ptr.ctypes.data), hg.hot_ptr.nbytes)
-                ctx.call("gcnb_h2d", _ptr(self.hot_idx), C.c_void_p(hg.hot_cols_p.ctypes.data), hg.hot_cols_p.nbytes)
             lo, hi = int(hg.hot_ptr[a]), int(hg.hot_ptr[b])
-            if hi > lo:
-                ctx.call("gcnb_h2d", at(self.hot_col16, 2 * lo), C.c_void_p(hg.hot_col.ctypes.data + 2 * lo), 2 * (hi - lo))
-                lo8 = lo & ~7
-                ctx.call("gcnb_expand_u16_i32", at(self.hot_col16, 2 * lo8), hi - lo8, at(self.hot_csr[1], 4 * lo8))
-                ctx.call("gcnb_h2d", at(self.hot_csr[2], 4 * lo), C.c_void_p(hg.hot_val.ctypes.data + 4 * lo), 4 * (hi - lo))
-            if b > a:
-                ctx.call("gcnb_csr_to_dense_f32", at(self.hot_csr[0], 4 * a), _ptr(self.hot_csr[1]), _ptr(self.hot_csr[2]),
-                         b - a, hg.kh, at(self.X_hot, 4 * a * hg.kh), hg.kh)
+            if phase in ("copy", "both"):
+                if first:
+                    ctx.call("gcnb_h2d", _ptr(self.hot_csr[0]), C.c_void_p(hg.hot_ptr.ctypes.data), hg.hot_ptr.nbytes)
+                    ctx.call("gcnb_h2d", _ptr(self.hot_idx), C.c_void_p(hg.hot_cols_p.ctypes.data), hg.hot_cols_p.nbytes)
+                if hi > lo:
+                    ctx.call("gcnb_h2d", at(self.hot_col16, 2 * lo), C.c_void_p(hg.hot_col.ctypes.data + 2 * lo), 2 * (hi - lo))
+                    ctx.call("gcnb_h2d", at(self.hot_csr[2], 4 * lo), C.c_void_p(hg.hot_val.ctypes.data + 4 * lo), 4 * (hi - lo))
+            if phase in ("expand", "both"):
+                if hi > lo:
+                    lo8 = lo & ~7
+                    ctx.call("gcnb_expand_u16_i32", at(self.hot_col16, 2 * lo8), hi - lo8, at(self.hot_csr[1], 4 * lo8))
+                if b > a:
+                    ctx.call("gcnb_csr_to_dense_f32", at(self.hot_csr[0], 4 * a), _ptr(self.hot_csr[1]), _ptr(self.hot_csr[2]),
+                             b - a, hg.kh, at(self.X_hot, 4 * a * hg.kh), hg.kh)
             return
         # the hot block travels as CSR (hot-local column ids) and is expanded to the dense N x Kh operand on the device
         for dst, src in zip(self.hot_csr, (hg.hot_ptr, hg.hot_col, hg.hot_val)):
@@ -1202,7 +1210,9 @@ class Engine:
                 self.stream.wait_event(ev)
                 a, b = rb[g], rb[g + 1]
                 at = lambda t, off: C.c_void_p(t.data_ptr() + off)
+                self.X.refill_rows(self, self.host.X, a, b, self.ctx, first=False, phase="expand")
                 if self.kh:
+                    self._upload_hot(self.host, self.ctx, rows=(a, b), first=False, phase="expand")
                     if g == 0:
                         self.ctx.call("gcnb_gather_rows_f32", W0, ldw0, _ptr(self.hot_idx), self.kh, hd,
                                       _ptr(self.W0_hot), self.ldh[0])
