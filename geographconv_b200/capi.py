@@ -151,7 +151,7 @@ class Context:
             self.set_option("gemm_blo", int(os.environ["GCNB_GEMM_BLO"]))
         if "GCNB_GEMM_V" in os.environ:  # tcgen05 GEMM kernel: 2 = two co-resident CTAs per SM (default), 1 = one per SM
             self.set_option("gemm_v", int(os.environ["GCNB_GEMM_V"]))
-        if "GCNB_GEMM_BLO2" in os.environ:  # gemm_v 2: weights' residual tile derived in shared memory (1, default) or loaded (0)
+        if "GCNB_GEMM_BLO2" in os.environ:  # gemm_v 2: weights' residual tile derived in shared memory (1) or loaded (0, default)
             self.set_option("gemm_blo2", int(os.environ["GCNB_GEMM_BLO2"]))
         if "GCNB_GEMM_PREFETCH" in os.environ:  # gemm_v 2: L2 look-ahead of the activation rows, in 128-row tiles
             self.set_option("gemm_prefetch", int(os.environ["GCNB_GEMM_PREFETCH"]))

@@ -50,7 +50,9 @@ struct gcnb_ctx {
   int gemm_v = 2;        // tcgen05 GEMM kernel: 2 = two co-resident CTAs per SM (k-blocks of 16), 1 = one tile per SM (k-blocks of 32)
   int gemm_prefetch = 0;   // gemm_v 2: L2 look-ahead of the activation rows in 128-row tiles (-1 = what the grid has in flight; measured
                            // slower than the plain demand loads: off)
-  int gemm_blo2 = 1;       // gemm_v 2: weights' residual tile derived in shared memory (1) or loaded pre-split from L2 (0)
+  int gemm_blo2 = 0;       // gemm_v 2: weights' residual tile derived in shared memory (1) or loaded pre-split from L2 (0).  Measured
+                           // (profiles/r2h_gemm_bench*.txt): 1 is 5% slower -- the kernel is bound by shared-memory bandwidth, and the
+                           // extra converter traffic costs more than the TMA bytes it saves
   int gemm_blo = 0;      // 1: tcgen05 GEMMs derive the weights' lo tile in shared memory instead of loading it from L2
   int tc_launches = 0;
   int tc_dbg_mode = 0;
