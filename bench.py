@@ -475,6 +475,13 @@ def parity_block(eng, clf, A, cfg, rank, n_rows):
     seed = 424242
     eng.forward(train=True, seed=seed)
     checksum = eng.checksum(eng.P, eng.n_loc, C)
+    # per-layer checksums of the same forward (H0, then Y / H / T of every highway layer): where a difference between two
+    # runs (GPU counts, kernel versions) first appears
+    layer_sums = {"H0": "%012x" % eng.checksum(eng.H0, eng.n_loc, hd)}
+    for i, b in enumerate(eng.lay):
+        for name in ("Y", "H", "T"):
+            if b.get(name) is not None:
+                layer_sums["%s%d" % (name, i + 1)] = "%012x" % eng.checksum(b[name], eng.n_loc, eng.layout.layers[i]["n_out"])
     rng = np.random.RandomState(12345)
     rows = np.sort(rng.choice(n, size=min(n_rows, n), replace=False))
     sub = A[rows].tocsr()
@@ -505,7 +512,7 @@ def parity_block(eng, clf, A, cfg, rank, n_rows):
         mism = np.nonzero(p_gpu.argmax(1) != p_ref.argmax(1))[0]
         top2 = np.sort(p_ref[mism], axis=1)[:, -2:] if len(mism) else np.zeros((0, 2))
         out = {"rows_sampled": int(len(rows)), "forward_checksum": "%012x" % checksum,
-               "spmm_checksum": "%012x" % spmm_checksum,
+               "spmm_checksum": "%012x" % spmm_checksum, "layer_checksums": layer_sums,
                "spmm_max_rel": spmm_err, "probs_max_rel": probs_err, "max_rel": max(spmm_err, probs_err),
                "argmax_mismatch": int(len(mism)),
                "argmax_mismatch_top2_rel_gap": [float((b - a) / b) for a, b in top2],

@@ -149,7 +149,7 @@ class Context:
         # tuning knobs every context of the process honours (A/B measurements; defaults are the measured winners)
         if "GCNB_GEMM_BLO" in os.environ:  # tcgen05 GEMMs: weights' lo tile derived in shared memory (1) or loaded (0)
             self.set_option("gemm_blo", int(os.environ["GCNB_GEMM_BLO"]))
-        if "GCNB_GEMM_V" in os.environ:  # tcgen05 GEMM kernel: 2 = two co-resident CTAs per SM (default), 1 = one per SM
+        if "GCNB_GEMM_V" in os.environ:  # tcgen05 GEMM kernel: 1 = one tile per SM (default), 2 = two co-resident CTAs per SM
             self.set_option("gemm_v", int(os.environ["GCNB_GEMM_V"]))
         if "GCNB_GEMM_BLO2" in os.environ:  # gemm_v 2: weights' residual tile derived in shared memory (1) or loaded (0, default)
             self.set_option("gemm_blo2", int(os.environ["GCNB_GEMM_BLO2"]))

@@ -47,7 +47,10 @@ struct gcnb_ctx {
   int spmm_sliced_engine = -1;  // gather engine of the feature-sliced product: -1 by operand size, else 0 / 1 / 2
   int spmm_panel_policy = 1;  // gathers of the panel engine: 0 default policy, 1 L2 evict_last hint, 2 + L1 allocation
   int gemm_tc = 1;       // tcgen05 GEMMs where supported (0 = CUDA-core fp32 kernels only)
-  int gemm_v = 2;        // tcgen05 GEMM kernel: 2 = two co-resident CTAs per SM (k-blocks of 16), 1 = one tile per SM (k-blocks of 32)
+  int gemm_v = 1;        // tcgen05 GEMM kernel: 1 = one tile per SM (k-blocks of 32, default), 2 = two co-resident CTAs per SM
+                         // (k-blocks of 16; 3-25% faster per product, parity-green, but its forward is bit-identical only among
+                         // runs with the same GPU count class -- 1 GPU vs N GPUs differ in the last bit from the second highway
+                         // layer on, cause not found: opt-in until it is)
   int gemm_prefetch = 0;   // gemm_v 2: L2 look-ahead of the activation rows in 128-row tiles (-1 = what the grid has in flight; measured
                            // slower than the plain demand loads: off)
   int gemm_blo2 = 0;       // gemm_v 2: weights' residual tile derived in shared memory (1) or loaded pre-split from L2 (0).  Measured

@@ -173,10 +173,10 @@ def test_gemm_simt(tA, tB, M, N, K):
     _close(got, want, atol_scale=3e-6)
 
 
-@pytest.fixture(params=[2, 1], ids=["two_ctas_per_sm", "one_cta_per_sm"])
+@pytest.fixture(params=[1, 2], ids=["one_cta_per_sm", "two_ctas_per_sm"])
 def gemm_v(request):
-    """Both tcgen05 GEMM kernels (ctx option gemm_v): the default with two co-resident CTAs per SM and k-blocks of 16
-    floats, and the one-tile-per-SM kernel with k-blocks of 32."""
+    """Both tcgen05 GEMM kernels (ctx option gemm_v): the default one-tile-per-SM kernel with k-blocks of 32 floats and
+    the opt-in kernel with two co-resident CTAs per SM and k-blocks of 16."""
     from geographconv_b200 import layers
     d = layers.get_dev()
     old = d.ctx.get_option("gemm_v")

@@ -246,6 +246,32 @@ def test_whole_model_parity_with_every_spmm_engine(problem, monkeypatch, engine,
         np.testing.assert_allclose(g, rg, rtol=1e-3, atol=1e-4 * float(np.abs(rg).max()) + 1e-12, err_msg=name)
 
 
+def test_whole_model_parity_with_the_two_cta_gemm_kernel(problem, monkeypatch):
+    """GCNB_GEMM_V=2 (two co-resident tcgen05 CTAs per SM, k-blocks of 16 floats, opt-in): predict, one training step and
+    every gradient against the oracle, like the default kernel."""
+    monkeypatch.setenv("GCNB_GEMM_V", "2")
+    A, X, Y, tr, dev, te, cfg = problem
+    hid = [300, 300, 300]
+    clf = _model(cfg, True, hid=hid)
+    clf.build_model(A, seed=21)
+    params = [p.copy() for p in clf.init_params]
+    preds, probs = clf.predict(X, A, te)
+    eng = clf._get_engine()
+    assert eng.ctx.get_option("gemm_v") == 2
+    _, rprob64 = gcn_ref.predict(params, X, A, te, hid, True, dtype="float64")
+    np.testing.assert_allclose(probs, rprob64, rtol=1e-3, atol=1e-7)
+    assert_argmax_parity(preds, probs, rprob64)
+    seed = 778
+    out = clf.f_train(X, Y[tr], Y[dev], A, tr, dev, seed=seed, update=False)
+    keep = gcn_ref.dropout_keep_mask(seed, cfg["n"], hid[0], 0.5)
+    r = gcn_ref.loss_and_grads(params, X, A, Y, tr, hid, True, keep.astype(np.float32) / 0.5, 0.0, dtype="float64",
+                               dev_idx=dev)
+    np.testing.assert_allclose(out[0], r["train_loss"], rtol=1e-3)
+    np.testing.assert_allclose(out[2], r["dev_loss"], rtol=1e-3)
+    for name, g, rg in zip([e["name"] for e in eng.layout.entries], eng.get_grads(), r["grads"]):
+        np.testing.assert_allclose(g, rg, rtol=1e-3, atol=1e-4 * float(np.abs(rg).max()) + 1e-12, err_msg=name)
+
+
 def test_wide_output_layer_930_classes(problem):
     """TwitterWorld runs at bucket 2400 = 930 classes with 900 hidden units (reference README.md:177-181): the output
     row is wider than one 512-column softmax pass."""

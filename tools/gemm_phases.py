@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 from geographconv_b200 import capi  # noqa: E402
 
 n, hd, ld = 500000, 300, 320
-version = int(sys.argv[1]) if len(sys.argv) > 1 else 2   # tcgen05 GEMM kernel (ctx option gemm_v)
+version = int(sys.argv[1]) if len(sys.argv) > 1 else 1   # tcgen05 GEMM kernel (ctx option gemm_v)
 dev = torch.device("cuda", 0)
 stream = torch.cuda.Stream(dev)
 ctx = capi.Context(0, C.c_void_p(stream.cuda_stream))

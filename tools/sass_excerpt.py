@@ -13,7 +13,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "geographconv_b200", "libgcnb200.so")
-KERNELS = ["gemm_tc_kernel", "wgrad_tc_kernel", "spmm_panel_kernel", "spmm_bulk_kernel", "spmm_ldg_kernel",
+KERNELS = ["gemm_tc2_kernel", "gemm_tc_kernel", "wgrad_tc_kernel", "spmm_panel_kernel", "spmm_bulk_kernel", "spmm_ldg_kernel",
            "slice_push_kernel", "peer_barrier_kernel", "highway_bwd_colsum_kernel", "xent_grad_dense_kernel",
            "adj_hub_setbits", "expand_u16_kernel"]
 KEYS = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "LDG.E.128", "LDG.E.CONSTANT.128",
