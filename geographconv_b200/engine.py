@@ -147,6 +147,7 @@ class HostCsr:
         self.shape = tuple(int(x) for x in M.shape)
         self.nnz = int(M.nnz)
         rowptr = np.ascontiguousarray(M.indptr, dtype=np.int32)
+        self.row_bounds = [0, self.shape[0]]  # row groups of the item plan (one group unless ``row_groups`` > 1)
         if col_blocks > 1 and M.nnz:
             items, long_rows, n_slots = plan_col_blocks(rowptr, M.indices, self.shape[1], int(col_blocks), int(chunk))
         else:
@@ -159,8 +160,6 @@ class HostCsr:
             # Row groups (X only): the items of consecutive row ranges are kept together, longest first inside a group,
             # so that a product can also be launched group by group while the later rows are still crossing PCIe
             # (Engine.bind's repeated uploads).  One launch over all items computes the same thing.
-            self.row_bounds = [0, self.shape[0]]
-            self.item_bounds = [0, len(items)]
             if row_groups > 1 and len(long_rows) == 0 and self.shape[0] >= 64 * row_groups:
                 per = -(-self.shape[0] // int(row_groups))
                 per = -(-per // 128) * 128  # whole 128-row GEMM tiles
@@ -170,8 +169,8 @@ class HostCsr:
                 self.item_bounds = [0] + list(np.cumsum(np.bincount(gid, minlength=len(self.row_bounds) - 1)))
             elif len(lens) and int(lens.max()) > int(lens.min()):
                 items = np.ascontiguousarray(items[np.argsort(-lens, kind="stable")])
-        if not hasattr(self, "row_bounds"):
-            self.row_bounds, self.item_bounds = [0, self.shape[0]], [0, len(items)]
+        if len(self.row_bounds) == 2:
+            self.item_bounds = [0, len(items)]
         self.col_blocks = int(col_blocks)
         self.rowptr = _pinned(rowptr)
         self.colidx = _pinned(np.ascontiguousarray(M.indices, dtype=np.int32))
@@ -550,6 +549,8 @@ class Engine:
         self.side_ws = None
         self._side_readers = {}   # data_ptr of a buffer -> event after which the side stream no longer reads it
         self._uploads = {}
+        self._uploads_pending = False   # bind(force_upload) on a cached graph: forward() issues the copies
+        self._x_group_events = []       # one event per row group of X while those copies are in flight
         # exchange design of the graph convolutions (module docstring); "slice" needs CUDA IPC between the ranks.
         # "auto" (default) decides per bound graph: sliced while this rank's 32-column panel of the operand (N x 128 B)
         # stays L2-resident, the all-gather + row-block product otherwise (measured at N = 2M, Hd = 512 on 8 GPUs:
@@ -1206,14 +1207,14 @@ class Engine:
         W0, ldw0 = self._pptr("W0")
         b0, _ = self._pptr("b0")
         p = self.drop_out if train else 0.0
-        if getattr(self, "_uploads_pending", False):
+        if self._uploads_pending:
             self._issue_uploads()
         self._wait_upload("X")
         # SparseInputDenseLayer + dropout: one SpMM with bias/act/dropout fused in the epilogue; when X has a
         # dense hot-column block, X_hot . W0[hot] runs on the tensor cores first and the cold-column SpMM adds to it
         # a highway layer convolves H0 itself (S = A.H0): its column slices leave from this kernel's epilogue
         want_push = bool(L.layers and L.layers[0]["kind"] == "hw")
-        group_events, self._x_group_events = getattr(self, "_x_group_events", []), []
+        group_events, self._x_group_events = self._x_group_events, []
         if group_events:
             # X is still crossing PCIe in row groups (bind with force_upload): the first layer follows the copies group
             # by group -- same kernels, same per-row arithmetic, items of one row group per launch
